@@ -1,0 +1,181 @@
+/*
+ * b200lda.h — C ABI of libb200lda.so: a B200-native (sm_100a) collapsed-Gibbs LDA sampler.
+ *
+ * Drop-in boundary. The reference (qianjinding/LDAGibbsSampling) has no FFI of its own; its hot
+ * path is the used subset of Mallet 2.0.7's cc.mallet.topics.ParallelTopicModel /
+ * TopicInferencer (un-vendored jar, reference pom.xml:107-111) driven from exactly two places:
+ * cmu_ron/TrainAndPredict.java:159-177 and cmu/TrainAndPredict.java:258-274. Every entry point
+ * below names the Java call it stands behind; java/B200TopicModel.java (Panama FFM) and
+ * ldagibbssampling_b200/topic_model.py (ctypes) bind exactly these symbols.
+ *
+ * Conventions
+ *  - plain C, no exceptions across the boundary; every call returns B200LDA_OK (0) or a negative
+ *    b200lda_status; b200lda_last_error() gives the message of the calling thread's last failure;
+ *  - every pointer argument is a HOST pointer unless its name starts with d_; input buffers are
+ *    borrowed for the duration of the call only, output buffers are caller-allocated and
+ *    caller-owned;
+ *  - a context is single-caller (one host thread drives it) and owns one GPU; AD-LDA across
+ *    GPUs = one context per GPU (one process per GPU, or several contexts in one process) plus
+ *    one integer all-reduce per sweep between b200lda_sweep_begin and b200lda_sweep_end;
+ *  - there is NO CPU fallback: b200lda_create fails with B200LDA_ENODEV without an sm_100 GPU.
+ *
+ * Sampling semantics ("sampling spec"): per token
+ *      p(z=k) ∝ (n_wk^{-i} + beta) (n_dk^{-i} + alpha_k) / (n_k + V beta)
+ * i.e. the conditional Mallet's WorkerRunnable.sampleTopicsForOneDoc draws from, evaluated as
+ * a sparse doc bucket n_dk(n_wk+beta)/(n_k+V beta) over the document's non-zero topics plus a
+ * per-word prior bucket alpha_k(n_wk+beta)/(n_k+V beta) resolved through a prefix table built at
+ * the start of the sweep; n_k is the sweep-start snapshot. Randomness: Philox4x32-10,
+ * key = seed, counter = (global token index, sweep, stream) — independent of sharding.
+ */
+#ifndef B200LDA_H
+#define B200LDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LDA_ABI_VERSION 1
+
+typedef enum {
+  B200LDA_OK = 0,
+  B200LDA_EINVAL = -1,   /* bad argument (IllegalArgumentException in the Java shim)      */
+  B200LDA_ENODEV = -2,   /* no sm_100 device / device ordinal out of range                */
+  B200LDA_ENOMEM = -3,   /* device or pinned-host allocation failed                       */
+  B200LDA_ECUDA = -4,    /* a CUDA call or kernel failed; context is unusable afterwards  */
+  B200LDA_ESTATE = -5,   /* call order violated (e.g. sweep before load_corpus)           */
+  B200LDA_ERANGE = -6    /* word id >= V, topic >= K, document longer than 65535 tokens   */
+} b200lda_status;
+
+typedef enum {
+  /* n_wk is updated in place with integer atomics while other documents read it (closest to
+   * Mallet's single-thread chain; run-to-run non-deterministic across documents). */
+  B200LDA_MODE_LIVE = 0,
+  /* n_wk / n_k are frozen for the whole sweep and the moves are applied at its end (AD-LDA with
+   * one "processor" per document). Bit-reproducible, independent of the number of GPUs, and
+   * reproduced exactly by the CPU oracle. */
+  B200LDA_MODE_DEFERRED = 1
+} b200lda_mode;
+
+typedef struct b200lda_ctx b200lda_ctx;
+
+typedef struct {
+  int32_t struct_size;          /* = sizeof(b200lda_config); guards ABI drift                  */
+  int32_t num_topics;           /* K, 1..65536       ParallelTopicModel(int K, ...)            */
+  int32_t num_types;            /* V = alphabet size at addInstances                          */
+  int32_t mode;                 /* b200lda_mode                                               */
+  double alpha_sum;             /* ParallelTopicModel ctor arg 2 (alpha_k = alpha_sum / K)    */
+  double beta;                  /* ParallelTopicModel ctor arg 3                              */
+  uint64_t seed;                /* setRandomSeed(int) analogue (Philox key)                   */
+  int32_t device;               /* CUDA ordinal                                               */
+  int32_t rank;                 /* AD-LDA shard id, 0..world_size-1                           */
+  int32_t world_size;           /* number of shards (setNumThreads(n) analogue), >= 1         */
+  int32_t reserved0;
+  int64_t global_token_offset;  /* global index of this shard's first token (Philox counter)  */
+  int64_t global_doc_offset;    /* global index of this shard's first document                */
+  void* stream;                 /* cudaStream_t to enqueue on, or NULL to create a private one */
+} b200lda_config;
+
+typedef struct {
+  int64_t num_docs, num_tokens;
+  int64_t sweeps_done;            /* total sweeps sampled so far                              */
+  int64_t kernel_launches;        /* kernels launched by this context since create            */
+  int64_t tokens_sampled;         /* sum over sweeps of tokens resampled                      */
+  double last_sweep_ms;           /* device time of the last sweep (tables+sample+finish)     */
+  double last_tables_ms;          /* ... of which per-sweep table build                       */
+  double last_sample_ms;          /* ... of which the sampling kernel                         */
+  double last_finish_ms;          /* ... of which delta/apply                                 */
+  double mean_doc_topics;         /* token-weighted mean #non-zero doc topics (K_d bar)       */
+  int64_t tokens_moved_last;      /* tokens whose topic changed in the last sweep             */
+  int64_t prior_bucket_last;      /* tokens resolved through the prior table in the last sweep */
+  int64_t device_bytes;           /* device memory held                                       */
+  int32_t smem_bytes_per_cta, warps_per_cta, ctas, slot_capacity;
+} b200lda_stats;
+
+/* Message of the calling thread's most recent failure ("" if none). Never NULL. */
+const char* b200lda_last_error(void);
+int b200lda_abi_version(void);
+/* Number of visible sm_100 devices (0 if none / no driver); never fails. */
+int b200lda_device_count(void);
+
+/* new ParallelTopicModel(K, alphaSum, beta)                cmu_ron/TrainAndPredict.java:160,
+ *                                                          cmu/TrainAndPredict.java:259 */
+int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out);
+void b200lda_destroy(b200lda_ctx* ctx);
+
+/* model.addInstances(InstanceList) — corpus half           cmu_ron/TrainAndPredict.java:162,
+ * Flattened FeatureSequences: doc d = tok_word[doc_ptr[d] .. doc_ptr[d+1]).   cmu/…:260
+ * Copies to the device and packs the doc->token and word->token CSR orders. Replaces any
+ * corpus already loaded (updateModel: pass old + new documents, cmu_ron/…:173-177). */
+int b200lda_load_corpus(b200lda_ctx* ctx, int64_t num_docs, const int64_t* doc_ptr,
+                        const int32_t* tok_word);
+/* model.addInstances(InstanceList) — assignment half: z == NULL draws the uniform random
+ * initial topics on the device (Mallet: random.nextInt(K) per token); z != NULL installs the
+ * caller's topics (seed-matched init from another sampler, or a restored checkpoint). Builds
+ * n_wk, n_k and the sparse n_dk rows. */
+int b200lda_init_assignments(b200lda_ctx* ctx, const int32_t* z);
+
+/* model.estimate() for n sweeps (setNumIterations(n))      cmu_ron/TrainAndPredict.java:165-166,
+ * Single-shard contexts only (world_size == 1); blocks until done.            cmu/…:263,265 */
+int b200lda_sweep(b200lda_ctx* ctx, int32_t n);
+
+/* One AD-LDA sweep of a multi-shard model (setNumThreads(n), cmu_ron/…:164, cmu/…:262; replaces
+ * WorkerRunnable.run + ParallelTopicModel.sumTypeTopicCounts):
+ *   sweep_begin  enqueues table build + sampling + delta formation;
+ *   the caller sums the exchange buffer (int32, *count elements, device memory) over all shards
+ *     in place — ncclAllReduce(ncclInt32, ncclSum) on the context's stream, or any equivalent;
+ *   sweep_end    applies the summed delta to the n_wk / n_k replicas.
+ * Neither call synchronises; use b200lda_synchronize. Also valid with world_size == 1. */
+int b200lda_sweep_begin(b200lda_ctx* ctx);
+int b200lda_exchange_buffer(b200lda_ctx* ctx, void** d_buf, int64_t* count);
+int b200lda_sweep_end(b200lda_ctx* ctx);
+int b200lda_synchronize(b200lda_ctx* ctx);
+int b200lda_get_stream(b200lda_ctx* ctx, void** stream);
+
+/* Frozen-snapshot parity mode (north star; no Java counterpart): resample every token once
+ * against the current counts WITHOUT moving any count. uniforms == NULL uses Philox with the
+ * given sweep number; otherwise uniforms[i] in [0,1) is token i's draw. */
+int b200lda_sample_frozen(b200lda_ctx* ctx, const float* uniforms, uint32_t sweep, int32_t* z_out);
+
+/* model.modelLogLikelihood()                               cmu_ron/TrainAndPredict.java:234,
+ * world_size > 1: *out is this shard's document part plus the (replicated)    cmu/…:436
+ * word/topic part; b200lda_loglik_parts separates them so the caller can sum document parts. */
+int b200lda_loglik(b200lda_ctx* ctx, double* out);
+int b200lda_loglik_parts(b200lda_ctx* ctx, double* doc_part, double* word_part);
+
+/* model.data.get(d).topicSequence.getFeatures()            cmu_ron/TrainAndPredict.java:135-143 */
+int b200lda_get_assignments(b200lda_ctx* ctx, int32_t* z /* num_tokens, document order */);
+/* typeTopicCounts / tokensPerTopic (dense)                 used by getInferencer(), cmu_ron/…:169 */
+int b200lda_get_nwk(b200lda_ctx* ctx, int32_t* nwk /* V*K, row-major by word */);
+int b200lda_get_nk(b200lda_ctx* ctx, int32_t* nk /* K */);
+/* Sparse doc-topic rows, topics ascending: row d = [row_ptr[d], row_ptr[d]+nnz). Pass topic ==
+ * NULL to only size: row_ptr (num_docs+1 entries) is filled either way. */
+int b200lda_get_ndk_csr(b200lda_ctx* ctx, int64_t* row_ptr, int32_t* topic, int32_t* count);
+/* model.getTopicProbabilities(topicSequence)               cmu_ron/TrainAndPredict.java:143,
+ * theta for documents [doc_begin, doc_end): (doc_end-doc_begin)*K doubles.    cmu/…:113 */
+int b200lda_get_theta(b200lda_ctx* ctx, int64_t doc_begin, int64_t doc_end, double* theta);
+/* phi_kw = (n_wk+beta)/(n_k+V beta): K*V doubles, row-major by topic (printTopWords input,
+ * cmu_ron/TrainAndPredict.java:231). */
+int b200lda_get_phi(b200lda_ctx* ctx, double* phi);
+
+/* Hyper-parameters (host-side optimisation hooks; setOptimizeInterval(20) cmu_ron/…:163). */
+int b200lda_set_alpha(b200lda_ctx* ctx, const double* alpha /* K */);
+int b200lda_get_alpha(b200lda_ctx* ctx, double* alpha /* K */);
+int b200lda_set_beta(b200lda_ctx* ctx, double beta);
+
+/* Checkpoint/resume hooks (replaces Java serialisation, cmu_ron/TrainAndPredict.java:179-200):
+ * sweep counter continues the Philox stream of a restored chain. */
+int b200lda_set_sweep_counter(b200lda_ctx* ctx, int64_t sweeps_done);
+
+int b200lda_get_stats(b200lda_ctx* ctx, b200lda_stats* out);
+
+/* Pinned host staging memory for callers whose runtime cannot pin its own (JVM heaps). */
+int b200lda_host_alloc(void** out, size_t bytes);
+int b200lda_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LDA_H */

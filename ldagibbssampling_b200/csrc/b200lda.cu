@@ -1,0 +1,899 @@
+// b200lda.cu — host runtime + C ABI of libb200lda.so (include/b200lda.h).
+//
+// One context = one GPU = one AD-LDA shard. The runtime owns the device-resident corpus (CSR
+// doc->token and word->token orders), the count state (n_wk dense int32 V x K, n_k, packed n_dk
+// rows), the per-sweep tables and one CUDA stream on which every kernel is enqueued.
+// There is no CPU fallback anywhere in this file: without an sm_100 device create() fails.
+#include "../../include/b200lda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "device_common.cuh"
+#include "loglik_kernels.cuh"
+#include "pack_kernels.cuh"
+#include "sweep_kernel.cuh"
+#include "table_kernels.cuh"
+
+using namespace b200lda;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(e__ == cudaErrorMemoryAllocation ? B200LDA_ENOMEM : B200LDA_ECUDA,      \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != B200LDA_OK) return rc__; \
+  } while (0)
+
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+constexpr int kStatCounters = 8;  // [0] doc scheduler, [1] moved, [2] prior draws, [3] nnz sum, [4] nnz(n_wk)
+
+int round_up32(int x) { return (x + 31) & ~31; }
+
+PriorLayout make_layout(int K) {
+  PriorLayout L{};
+  int sizes[5], n = 0;
+  sizes[n++] = K;
+  while (sizes[n - 1] > 32 && n < 5) {
+    sizes[n] = (sizes[n - 1] + 31) / 32;
+    ++n;
+  }
+  L.nlev = n;
+  int off = 0;
+  for (int i = 0; i < n; ++i) {
+    L.off[i] = off;
+    L.size[i] = sizes[i];
+    off += round_up32(sizes[i]);
+  }
+  L.stride = off;
+  return L;
+}
+
+}  // namespace
+
+struct b200lda_ctx {
+  b200lda_config cfg{};
+  int K = 0, V = 0;
+  int64_t D = 0, N = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  int64_t device_bytes = 0;
+  int64_t launches = 0;
+
+  // corpus
+  int64_t* d_doc_ptr = nullptr;
+  int32_t* d_tok_word = nullptr;
+  uint16_t* d_z = nullptr;
+  long long* d_word_ptr = nullptr;
+  int64_t* d_wtok = nullptr;
+  int64_t* d_row_ptr = nullptr;
+  int32_t* d_row_nnz = nullptr;
+  uint32_t* d_rows = nullptr;
+  int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
+  std::vector<int64_t> h_doc_ptr, h_row_ptr;
+  int max_doc_len = 0;
+
+  // counts + tables
+  int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
+  float *d_invden = nullptr, *d_ab = nullptr, *d_prior = nullptr, *d_q = nullptr, *d_alpha_f = nullptr;
+  double *d_alpha = nullptr, *d_lg_alpha = nullptr;
+  std::vector<double> alpha;
+  double alpha_sum = 0.0, beta = 0.0;
+  PriorLayout layout{};
+
+  // scratch
+  unsigned long long* d_counters = nullptr;
+  int* d_bad = nullptr;
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  double* d_partial = nullptr;  // [2 * kPartial + 2]
+  uint32_t* d_hist_scratch = nullptr;
+  size_t hist_scratch_bytes = 0;
+
+  // sweep launch shape
+  int slot_cap = 32, warps_per_cta = 8, ctas = 0;
+  size_t smem = 0;
+  bool tables_in_smem = true;
+
+  // state
+  bool corpus_loaded = false, assigned = false, in_sweep = false;
+  int64_t sweeps_done = 0, tokens_sampled = 0;
+  unsigned long long last_moved = 0, last_prior = 0, last_nnz_sum = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+};
+
+namespace {
+
+constexpr int kPartial = 1184;  // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
+
+int dev_alloc(b200lda_ctx* c, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200LDA_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  c->device_bytes += (int64_t)bytes;
+  return B200LDA_OK;
+}
+template <typename T>
+int dev_alloc_t(b200lda_ctx* c, T** p, size_t count) {
+  return dev_alloc(c, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <typename T>
+void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int ensure_stage(b200lda_ctx* c, size_t bytes) {
+  if (bytes <= c->stage_bytes) return B200LDA_OK;
+  if (c->d_stage) {
+    cudaFree(c->d_stage);
+    c->device_bytes -= (int64_t)c->stage_bytes;
+    c->d_stage = nullptr;
+    c->stage_bytes = 0;
+  }
+  TRY(dev_alloc(c, &c->d_stage, bytes));
+  c->stage_bytes = bytes;
+  return B200LDA_OK;
+}
+
+int grid_for(b200lda_ctx* c, int64_t work_items, int block, int per_sm = 8) {
+  int64_t blocks = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)c->sm_count * per_sm;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+int enter(b200lda_ctx* c) {
+  if (!c) return fail(B200LDA_EINVAL, "null context");
+  CU(cudaSetDevice(c->cfg.device));
+  return B200LDA_OK;
+}
+
+int push_alpha(b200lda_ctx* c) {
+  std::vector<float> af(c->K);
+  std::vector<double> lga(c->K);
+  c->alpha_sum = 0.0;
+  for (int k = 0; k < c->K; ++k) {
+    af[k] = (float)c->alpha[k];
+    lga[k] = std::lgamma(c->alpha[k]);
+    c->alpha_sum += c->alpha[k];
+  }
+  CU(cudaMemcpyAsync(c->d_alpha_f, af.data(), sizeof(float) * c->K, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_alpha, c->alpha.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_lg_alpha, lga.data(), sizeof(double) * c->K, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+template <int MODE, bool TS>
+int set_sweep_attr(size_t smem) {
+  CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return B200LDA_OK;
+}
+
+// Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
+// of slot_cap entries each. slot_cap = min(K, longest document) rounded to a warp tile.
+int configure_sweep(b200lda_ctx* c) {
+  c->slot_cap = std::max(32, round_up32(std::min(c->K, std::max(1, c->max_doc_len))));
+  const size_t tab = 2 * sizeof(float) * (size_t)c->K;
+  const size_t per_warp = 8 * (size_t)c->slot_cap;
+  bool ok = false;
+  for (int ts = 1; ts >= 0 && !ok; --ts) {
+    for (int wpc = 8; wpc >= 1 && !ok; wpc >>= 1) {
+      const size_t need = (ts ? tab : 0) + per_warp * wpc;
+      if (need <= kMaxSmemPerCta) {
+        c->tables_in_smem = ts != 0;
+        c->warps_per_cta = wpc;
+        c->smem = need;
+        ok = true;
+      }
+    }
+  }
+  if (!ok)
+    return fail(B200LDA_ERANGE, "document rows of %d slots do not fit shared memory (K=%d, longest doc=%d)",
+                c->slot_cap, c->K, c->max_doc_len);
+  int occ_u = 0, occ_f = 0;
+  if (c->tables_in_smem) {
+    TRY((set_sweep_attr<MODE_UPDATE, true>(c->smem)));
+    TRY((set_sweep_attr<MODE_FROZEN, true>(c->smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_gibbs_sweep<MODE_UPDATE, true>,
+                                                     c->warps_per_cta * 32, c->smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_gibbs_sweep<MODE_FROZEN, true>,
+                                                     c->warps_per_cta * 32, c->smem));
+  } else {
+    TRY((set_sweep_attr<MODE_UPDATE, false>(c->smem)));
+    TRY((set_sweep_attr<MODE_FROZEN, false>(c->smem)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_gibbs_sweep<MODE_UPDATE, false>,
+                                                     c->warps_per_cta * 32, c->smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_gibbs_sweep<MODE_FROZEN, false>,
+                                                     c->warps_per_cta * 32, c->smem));
+  }
+  const int occ = std::max(1, std::min(occ_u, occ_f));
+  c->ctas = c->sm_count * occ;  // persistent grid: every CTA resident, documents fetched dynamically
+  return B200LDA_OK;
+}
+
+int build_tables(b200lda_ctx* c) {
+  const float beta_f = (float)c->beta;
+  const float vbeta = (float)c->V * beta_f;
+  k_topic_tables<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_alpha_f, vbeta, c->d_invden, c->d_ab);
+  k_prior_rows<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_nwk, c->d_ab, beta_f,
+                                                                            c->layout, c->d_prior, c->d_q);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  return B200LDA_OK;
+}
+
+SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_write, uint32_t sweep) {
+  SweepParams p{};
+  p.num_docs = c->D;
+  p.doc_ptr = c->d_doc_ptr;
+  p.tok_word = c->d_tok_word;
+  p.z = c->d_z;
+  p.z_out = nullptr;
+  p.row_ptr = c->d_row_ptr;
+  p.row_nnz = c->d_row_nnz;
+  p.rows = c->d_rows;
+  p.nwk_read = nwk_read;
+  p.nwk_write = nwk_write;
+  p.nk_delta = c->d_nk_delta;
+  p.invden = c->d_invden;
+  p.ab = c->d_ab;
+  p.prior = c->d_prior;
+  p.q = c->d_q;
+  p.uniforms = nullptr;
+  p.layout = c->layout;
+  p.K = c->K;
+  p.slot_cap = c->slot_cap;
+  p.beta_f = (float)c->beta;
+  p.seed = c->cfg.seed;
+  p.sweep = sweep;
+  p.global_tok_off = c->cfg.global_token_offset;
+  p.doc_counter = c->d_counters + 0;
+  p.stats = c->d_counters + 1;
+  return p;
+}
+
+template <int MODE>
+int launch_sweep(b200lda_ctx* c, const SweepParams& p) {
+  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+  if (c->tables_in_smem)
+    k_gibbs_sweep<MODE, true><<<c->ctas, c->warps_per_cta * 32, c->smem, c->stream>>>(p);
+  else
+    k_gibbs_sweep<MODE, false><<<c->ctas, c->warps_per_cta * 32, c->smem, c->stream>>>(p);
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return B200LDA_OK;
+}
+
+int need_ready(b200lda_ctx* c) {
+  if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
+  if (!c->assigned) return fail(B200LDA_ESTATE, "no topic assignments (call b200lda_init_assignments)");
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  return B200LDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200lda_last_error(void) { return g_err.c_str(); }
+int b200lda_abi_version(void) { return B200LDA_ABI_VERSION; }
+
+int b200lda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
+  if (!cfg || !out) return fail(B200LDA_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(b200lda_config))
+    return fail(B200LDA_EINVAL, "b200lda_config.struct_size=%d, library expects %zu", cfg->struct_size,
+                sizeof(b200lda_config));
+  if (cfg->num_topics < 1 || cfg->num_topics > 65536) return fail(B200LDA_EINVAL, "num_topics must be in 1..65536");
+  if (cfg->num_types < 1) return fail(B200LDA_EINVAL, "num_types must be >= 1");
+  if (!(cfg->alpha_sum > 0.0) || !(cfg->beta > 0.0)) return fail(B200LDA_EINVAL, "alpha_sum and beta must be > 0");
+  if (cfg->mode != B200LDA_MODE_LIVE && cfg->mode != B200LDA_MODE_DEFERRED) return fail(B200LDA_EINVAL, "bad mode");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return fail(B200LDA_EINVAL, "bad rank/world_size");
+  if ((double)cfg->num_types * (double)cfg->num_topics > 8.0e9)
+    return fail(B200LDA_ERANGE, "V*K too large for a dense n_wk replica");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B200LDA_ENODEV, "no CUDA device visible; libb200lda has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(B200LDA_ENODEV, "device %d out of range (%d visible)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(B200LDA_ENODEV, "device %d is sm_%d%d; libb200lda is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  CU(cudaSetDevice(cfg->device));
+
+  b200lda_ctx* c = new (std::nothrow) b200lda_ctx();
+  if (!c) return fail(B200LDA_ENOMEM, "out of host memory");
+  c->cfg = *cfg;
+  c->K = cfg->num_topics;
+  c->V = cfg->num_types;
+  c->beta = cfg->beta;
+  c->sm_count = prop.multiProcessorCount;
+  c->layout = make_layout(c->K);
+  c->alpha.assign(c->K, cfg->alpha_sum / c->K);
+  int rc = B200LDA_OK;
+  auto bail = [&](int code) {
+    b200lda_destroy(c);
+    return code;
+  };
+  if (cfg->stream) {
+    c->stream = (cudaStream_t)cfg->stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+      return bail(fail(B200LDA_ECUDA, "cudaStreamCreate failed"));
+    c->own_stream = true;
+  }
+  for (auto& e : c->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(B200LDA_ECUDA, "cudaEventCreate failed"));
+  const size_t VK = (size_t)c->V * c->K;
+  const bool multi = cfg->world_size > 1;
+  if ((rc = dev_alloc_t(c, &c->d_nwk, VK)) || (rc = dev_alloc_t(c, &c->d_nk, c->K)) ||
+      (rc = dev_alloc_t(c, &c->d_nk_delta, c->K)) || (rc = dev_alloc_t(c, &c->d_invden, c->K)) ||
+      (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
+      (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
+      (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kStatCounters)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
+    return bail(rc);
+  if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
+    if ((rc = dev_alloc_t(c, &c->d_nwk_b, VK))) return bail(rc);
+  if (multi)
+    if ((rc = dev_alloc_t(c, &c->d_exchange, VK + c->K))) return bail(rc);
+  if (cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
+      cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kStatCounters, c->stream) != cudaSuccess)
+    return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
+  if ((rc = push_alpha(c))) return bail(rc);
+  *out = c;
+  return B200LDA_OK;
+}
+
+void b200lda_destroy(b200lda_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  dev_free(c->d_doc_ptr);
+  dev_free(c->d_tok_word);
+  dev_free(c->d_z);
+  dev_free(c->d_word_ptr);
+  dev_free(c->d_wtok);
+  dev_free(c->d_row_ptr);
+  dev_free(c->d_row_nnz);
+  dev_free(c->d_rows);
+  dev_free(c->d_nwk);
+  dev_free(c->d_nwk_b);
+  dev_free(c->d_nk);
+  dev_free(c->d_nk_delta);
+  dev_free(c->d_exchange);
+  dev_free(c->d_invden);
+  dev_free(c->d_ab);
+  dev_free(c->d_prior);
+  dev_free(c->d_q);
+  dev_free(c->d_alpha_f);
+  dev_free(c->d_alpha);
+  dev_free(c->d_lg_alpha);
+  dev_free(c->d_counters);
+  dev_free(c->d_bad);
+  dev_free(c->d_partial);
+  dev_free(c->d_hist_scratch);
+  if (c->d_stage) cudaFree(c->d_stage);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
+  delete c;
+}
+
+int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word) {
+  TRY(enter(c));
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  if (num_docs < 0 || !doc_ptr) return fail(B200LDA_EINVAL, "bad corpus arguments");
+  if (doc_ptr[0] != 0) return fail(B200LDA_EINVAL, "doc_ptr[0] must be 0");
+  const int64_t N = doc_ptr[num_docs];
+  if (N > 0 && !tok_word) return fail(B200LDA_EINVAL, "tok_word is null");
+  // host-side packing plan: row capacities min(K, L_d), longest document
+  c->h_doc_ptr.assign(doc_ptr, doc_ptr + num_docs + 1);
+  c->h_row_ptr.resize(num_docs + 1);
+  int max_len = 0;
+  int64_t off = 0;
+  for (int64_t d = 0; d < num_docs; ++d) {
+    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", (long long)d);
+    if (len > 65535) return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", (long long)d, (long long)len);
+    c->h_row_ptr[d] = off;
+    off += std::min<int64_t>(len, c->K);
+    max_len = std::max<int>(max_len, (int)len);
+  }
+  c->h_row_ptr[num_docs] = off;
+  c->corpus_loaded = false;
+  c->assigned = false;
+  if (num_docs > c->cap_docs) {
+    dev_free(c->d_doc_ptr);
+    dev_free(c->d_row_ptr);
+    dev_free(c->d_row_nnz);
+    TRY(dev_alloc_t(c, &c->d_doc_ptr, (size_t)num_docs + 1));
+    TRY(dev_alloc_t(c, &c->d_row_ptr, (size_t)num_docs + 1));
+    TRY(dev_alloc_t(c, &c->d_row_nnz, (size_t)num_docs));
+    c->cap_docs = num_docs;
+  }
+  if (N > c->cap_tokens) {
+    dev_free(c->d_tok_word);
+    dev_free(c->d_z);
+    dev_free(c->d_wtok);
+    TRY(dev_alloc_t(c, &c->d_tok_word, (size_t)N));
+    TRY(dev_alloc_t(c, &c->d_z, (size_t)N));
+    TRY(dev_alloc_t(c, &c->d_wtok, (size_t)N));
+    c->cap_tokens = N;
+  }
+  if (off > c->cap_rows) {
+    dev_free(c->d_rows);
+    TRY(dev_alloc_t(c, &c->d_rows, (size_t)off));
+    c->cap_rows = off;
+  }
+  if (!c->d_word_ptr) TRY(dev_alloc_t(c, &c->d_word_ptr, (size_t)c->V + 1));
+  c->D = num_docs;
+  c->N = N;
+  c->max_doc_len = max_len;
+  CU(cudaMemcpyAsync(c->d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_row_ptr, c->h_row_ptr.data(), sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
+  if (N > 0) CU(cudaMemcpyAsync(c->d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+  // word -> token CSR by counting sort; the histogram pass also validates word ids
+  TRY(ensure_stage(c, sizeof(unsigned long long) * (size_t)c->V));
+  unsigned long long* d_wcount = reinterpret_cast<unsigned long long*>(c->d_stage);
+  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  if (N > 0) k_word_hist<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, c->d_tok_word, d_wcount, c->d_bad);
+  k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>(c->V, d_wcount, c->d_word_ptr);
+  c->launches += 2;
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (bad) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
+  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
+  if (N > 0) {
+    k_word_scatter<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->d_tok_word, c->d_word_ptr, d_wcount, c->d_wtok);
+    c->launches += 1;
+  }
+  CU(cudaGetLastError());
+  TRY(configure_sweep(c));
+  CU(cudaStreamSynchronize(c->stream));
+  c->corpus_loaded = true;
+  return B200LDA_OK;
+}
+
+int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
+  TRY(enter(c));
+  if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  c->assigned = false;
+  const int64_t N = c->N;
+  if (N > 0) {
+    if (z) {
+      TRY(ensure_stage(c, sizeof(int32_t) * (size_t)N));
+      CU(cudaMemcpyAsync(c->d_stage, z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+      k_narrow_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, reinterpret_cast<const int32_t*>(c->d_stage),
+                                                          c->d_z, c->d_bad);
+      int bad = 0;
+      CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (bad) return fail(B200LDA_ERANGE, "z holds a topic outside [0, %d)", c->K);
+    } else {
+      k_init_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, c->cfg.seed, c->cfg.global_token_offset, c->d_z);
+    }
+    c->launches += 1;
+  }
+  // n_wk, n_k from the word -> token order
+  const size_t VK = (size_t)c->V * c->K;
+  CU(cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream));
+  CU(cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream));
+  CU(cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream));
+  if (N > 0) {
+    k_count_by_word<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_word_ptr, c->d_wtok,
+                                                                                c->d_z, c->d_nwk, c->d_nk);
+    c->launches += 1;
+  }
+  // sparse doc-topic rows
+  if (c->D > 0) {
+    const int wpc = 8;
+    const size_t hist_smem = sizeof(uint32_t) * (size_t)c->K * wpc;
+    const int grid = grid_for(c, c->D * 32, 256, hist_smem <= 48 * 1024 ? 8 : 2);
+    if (hist_smem <= 96 * 1024) {
+      CU(cudaFuncSetAttribute(k_build_doc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+      k_build_doc_rows<<<grid, wpc * 32, hist_smem, c->stream>>>(c->D, c->K, c->d_doc_ptr, c->d_z, c->d_row_ptr,
+                                                               c->d_row_nnz, c->d_rows, nullptr);
+    } else {
+      const size_t need = sizeof(uint32_t) * (size_t)c->K * wpc * grid;
+      if (need > c->hist_scratch_bytes) {
+        dev_free(c->d_hist_scratch);
+        TRY(dev_alloc(c, reinterpret_cast<void**>(&c->d_hist_scratch), need));
+        c->hist_scratch_bytes = need;
+      }
+      k_build_doc_rows<<<grid, wpc * 32, 0, c->stream>>>(c->D, c->K, c->d_doc_ptr, c->d_z, c->d_row_ptr, c->d_row_nnz,
+                                                       c->d_rows, c->d_hist_scratch);
+    }
+    c->launches += 1;
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->assigned = true;
+  return B200LDA_OK;
+}
+
+int b200lda_sweep_begin(b200lda_ctx* c) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  const bool multi = c->cfg.world_size > 1;
+  const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
+  const size_t VK = (size_t)c->V * c->K;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  TRY(build_tables(c));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  if (deferred || multi)
+    CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
+  // DEFERRED: read the frozen d_nwk, write moves into the copy d_nwk_b.
+  // LIVE:     read and write d_nwk in place (d_nwk_b keeps the sweep-start snapshot if multi).
+  SweepParams p = sweep_params(c, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
+  TRY(launch_sweep<MODE_UPDATE>(c, p));
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  if (multi) {
+    const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;
+    const int32_t* before = deferred ? c->d_nwk : c->d_nwk_b;
+    k_form_delta<<<grid_for(c, (int64_t)(VK / 4 + 1), 256), 256, 0, c->stream>>>(VK, c->K, after, before, c->d_nk_delta,
+                                                                                c->d_exchange);
+    c->launches += 1;
+    CU(cudaGetLastError());
+  }
+  c->in_sweep = true;
+  return B200LDA_OK;
+}
+
+int b200lda_exchange_buffer(b200lda_ctx* c, void** d_buf, int64_t* count) {
+  if (!c || !d_buf || !count) return fail(B200LDA_EINVAL, "null argument");
+  *d_buf = c->d_exchange;
+  *count = c->d_exchange ? (int64_t)((size_t)c->V * c->K + c->K) : 0;
+  return B200LDA_OK;
+}
+
+int b200lda_sweep_end(b200lda_ctx* c) {
+  TRY(enter(c));
+  if (!c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_end without b200lda_sweep_begin");
+  const bool multi = c->cfg.world_size > 1;
+  const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
+  const size_t VK = (size_t)c->V * c->K;
+  if (multi) {
+    const int32_t* before = deferred ? c->d_nwk : c->d_nwk_b;
+    k_apply_delta<<<grid_for(c, (int64_t)(VK / 4 + 1), 256), 256, 0, c->stream>>>(VK, c->K, c->d_nwk, before, c->d_exchange,
+                                                                                 c->d_nk, c->d_nk_delta);
+  } else {
+    if (deferred) std::swap(c->d_nwk, c->d_nwk_b);
+    k_apply_nk<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_nk_delta);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  c->ev_valid = true;
+  c->in_sweep = false;
+  c->sweeps_done += 1;
+  c->tokens_sampled += c->N;
+  return B200LDA_OK;
+}
+
+int b200lda_synchronize(b200lda_ctx* c) {
+  TRY(enter(c));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_get_stream(b200lda_ctx* c, void** stream) {
+  if (!c || !stream) return fail(B200LDA_EINVAL, "null argument");
+  *stream = (void*)c->stream;
+  return B200LDA_OK;
+}
+
+int b200lda_sweep(b200lda_ctx* c, int32_t n) {
+  TRY(enter(c));
+  if (n < 0) return fail(B200LDA_EINVAL, "negative sweep count");
+  if (c->cfg.world_size > 1)
+    return fail(B200LDA_ESTATE, "b200lda_sweep needs world_size == 1; shards use sweep_begin / all-reduce / sweep_end");
+  TRY(need_ready(c));
+  for (int32_t i = 0; i < n; ++i) {
+    TRY(b200lda_sweep_begin(c));
+    TRY(b200lda_sweep_end(c));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_sample_frozen(b200lda_ctx* c, const float* uniforms, uint32_t sweep, int32_t* z_out) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!z_out) return fail(B200LDA_EINVAL, "z_out is null");
+  const int64_t N = c->N;
+  if (N == 0) return B200LDA_OK;
+  TRY(ensure_stage(c, (size_t)N * 8));
+  int32_t* d_zout = reinterpret_cast<int32_t*>(c->d_stage);
+  float* d_u = reinterpret_cast<float*>(c->d_stage) + N;
+  if (uniforms) CU(cudaMemcpyAsync(d_u, uniforms, sizeof(float) * N, cudaMemcpyHostToDevice, c->stream));
+  TRY(build_tables(c));
+  SweepParams p = sweep_params(c, c->d_nwk, c->d_nwk_b ? c->d_nwk_b : c->d_nwk, sweep);
+  // distinct read/write pointers => read-only cached loads; MODE_FROZEN never writes counts
+  p.nwk_write = nullptr;
+  p.z_out = d_zout;
+  p.uniforms = uniforms ? d_u : nullptr;
+  TRY(launch_sweep<MODE_FROZEN>(c, p));
+  CU(cudaMemcpyAsync(z_out, d_zout, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_loglik_parts(b200lda_ctx* c, double* doc_part, double* word_part) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!doc_part || !word_part) return fail(B200LDA_EINVAL, "null argument");
+  const size_t VK = (size_t)c->V * c->K;
+  double* p_docs = c->d_partial;
+  double* p_words = c->d_partial + kPartial;
+  double* d_out = c->d_partial + 2 * kPartial;
+  unsigned long long* d_nz = c->d_counters + 4;
+  CU(cudaMemsetAsync(d_nz, 0, sizeof(unsigned long long), c->stream));
+  k_loglik_docs<<<kPartial, 256, 0, c->stream>>>(c->D, c->d_doc_ptr, c->d_row_ptr, c->d_row_nnz, c->d_rows, c->d_alpha,
+                                                c->d_lg_alpha, c->alpha_sum, p_docs);
+  k_loglik_words<<<kPartial, 256, 0, c->stream>>>(VK, c->d_nwk, c->beta, p_words, d_nz);
+  k_loglik_final<<<1, 256, 0, c->stream>>>(kPartial, p_docs, 0, c->d_nk, 0.0, d_out + 0);
+  k_loglik_final<<<1, 256, 0, c->stream>>>(kPartial, p_words, c->K, c->d_nk, c->beta * (double)c->V, d_out + 1);
+  c->launches += 4;
+  CU(cudaGetLastError());
+  double h[2];
+  unsigned long long nz = 0;
+  CU(cudaMemcpyAsync(h, d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&nz, d_nz, sizeof(nz), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *doc_part = h[0] + (double)c->D * std::lgamma(c->alpha_sum);
+  *word_part = h[1] + (double)c->K * std::lgamma(c->beta * (double)c->V) - (double)nz * std::lgamma(c->beta);
+  return B200LDA_OK;
+}
+
+int b200lda_loglik(b200lda_ctx* c, double* out) {
+  if (!out) return fail(B200LDA_EINVAL, "null argument");
+  double a = 0.0, b = 0.0;
+  TRY(b200lda_loglik_parts(c, &a, &b));
+  *out = a + b;
+  return B200LDA_OK;
+}
+
+int b200lda_get_assignments(b200lda_ctx* c, int32_t* z) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!z) return fail(B200LDA_EINVAL, "z is null");
+  const int64_t N = c->N;
+  if (N == 0) return B200LDA_OK;
+  TRY(ensure_stage(c, sizeof(int32_t) * (size_t)N));
+  int32_t* d_wide = reinterpret_cast<int32_t*>(c->d_stage);
+  k_widen_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->d_z, d_wide);
+  c->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(z, d_wide, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_get_nwk(b200lda_ctx* c, int32_t* nwk) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!nwk) return fail(B200LDA_EINVAL, "null argument");
+  CU(cudaMemcpyAsync(nwk, c->d_nwk, sizeof(int32_t) * (size_t)c->V * c->K, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_get_nk(b200lda_ctx* c, int32_t* nk) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!nk) return fail(B200LDA_EINVAL, "null argument");
+  CU(cudaMemcpyAsync(nk, c->d_nk, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_get_ndk_csr(b200lda_ctx* c, int64_t* row_ptr, int32_t* topic, int32_t* count) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!row_ptr) return fail(B200LDA_EINVAL, "row_ptr is null");
+  std::vector<int32_t> nnz((size_t)c->D);
+  if (c->D > 0) CU(cudaMemcpyAsync(nnz.data(), c->d_row_nnz, sizeof(int32_t) * c->D, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  row_ptr[0] = 0;
+  for (int64_t d = 0; d < c->D; ++d) row_ptr[d + 1] = row_ptr[d] + nnz[d];
+  if (!topic || !count) return B200LDA_OK;
+  const int64_t cap = c->h_row_ptr[c->D];
+  std::vector<uint32_t> rows((size_t)cap);
+  if (cap > 0) CU(cudaMemcpyAsync(rows.data(), c->d_rows, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int64_t d = 0; d < c->D; ++d) {
+    const uint32_t* src = rows.data() + c->h_row_ptr[d];
+    for (int32_t j = 0; j < nnz[d]; ++j) {
+      topic[row_ptr[d] + j] = (int32_t)(src[j] >> 16);
+      count[row_ptr[d] + j] = (int32_t)(src[j] & 0xffffu);
+    }
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_get_theta(b200lda_ctx* c, int64_t doc_begin, int64_t doc_end, double* theta) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (doc_begin < 0 || doc_end > c->D || doc_begin > doc_end) return fail(B200LDA_EINVAL, "bad document range");
+  if (doc_begin == doc_end) return B200LDA_OK;
+  if (!theta) return fail(B200LDA_EINVAL, "theta is null");
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(256u << 20) / (int64_t)(sizeof(double) * c->K));
+  for (int64_t d0 = doc_begin; d0 < doc_end; d0 += chunk) {
+    const int64_t d1 = std::min(doc_end, d0 + chunk);
+    TRY(ensure_stage(c, sizeof(double) * (size_t)(d1 - d0) * c->K));
+    double* d_theta = reinterpret_cast<double*>(c->d_stage);
+    k_theta<<<grid_for(c, (d1 - d0) * 32, 256), 256, 0, c->stream>>>(d0, d1, c->K, c->d_doc_ptr, c->d_row_ptr, c->d_row_nnz,
+                                                                    c->d_rows, c->d_alpha, c->alpha_sum, d_theta);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(theta + (size_t)(d0 - doc_begin) * c->K, d_theta, sizeof(double) * (size_t)(d1 - d0) * c->K,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_get_phi(b200lda_ctx* c, double* phi) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!phi) return fail(B200LDA_EINVAL, "phi is null");
+  const int kchunk = std::max<int>(32, (int)(((int64_t)(256u << 20) / (int64_t)(sizeof(double) * c->V)) / 32 * 32));
+  for (int k0 = 0; k0 < c->K; k0 += kchunk) {
+    const int k1 = std::min(c->K, k0 + kchunk);
+    TRY(ensure_stage(c, sizeof(double) * (size_t)(k1 - k0) * c->V));
+    double* d_phi = reinterpret_cast<double*>(c->d_stage);
+    dim3 grid((c->V + 31) / 32, (k1 - k0 + 31) / 32);
+    k_phi<<<grid, 256, 0, c->stream>>>(c->V, c->K, k0, k1, c->d_nwk, c->d_nk, c->beta, d_phi);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(phi + (size_t)k0 * c->V, d_phi, sizeof(double) * (size_t)(k1 - k0) * c->V, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_set_alpha(b200lda_ctx* c, const double* alpha) {
+  TRY(enter(c));
+  if (!alpha) return fail(B200LDA_EINVAL, "alpha is null");
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  for (int k = 0; k < c->K; ++k)
+    if (!(alpha[k] > 0.0)) return fail(B200LDA_EINVAL, "alpha[%d] must be > 0", k);
+  c->alpha.assign(alpha, alpha + c->K);
+  return push_alpha(c);
+}
+
+int b200lda_get_alpha(b200lda_ctx* c, double* alpha) {
+  if (!c || !alpha) return fail(B200LDA_EINVAL, "null argument");
+  std::copy(c->alpha.begin(), c->alpha.end(), alpha);
+  return B200LDA_OK;
+}
+
+int b200lda_set_beta(b200lda_ctx* c, double beta) {
+  if (!c) return fail(B200LDA_EINVAL, "null context");
+  if (!(beta > 0.0)) return fail(B200LDA_EINVAL, "beta must be > 0");
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  c->beta = beta;
+  return B200LDA_OK;
+}
+
+int b200lda_set_sweep_counter(b200lda_ctx* c, int64_t sweeps_done) {
+  if (!c) return fail(B200LDA_EINVAL, "null context");
+  if (sweeps_done < 0) return fail(B200LDA_EINVAL, "negative sweep counter");
+  c->sweeps_done = sweeps_done;
+  return B200LDA_OK;
+}
+
+int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
+  TRY(enter(c));
+  if (!out) return fail(B200LDA_EINVAL, "null argument");
+  memset(out, 0, sizeof(*out));
+  CU(cudaStreamSynchronize(c->stream));
+  out->num_docs = c->D;
+  out->num_tokens = c->N;
+  out->sweeps_done = c->sweeps_done;
+  out->kernel_launches = c->launches;
+  out->tokens_sampled = c->tokens_sampled;
+  out->device_bytes = c->device_bytes;
+  out->smem_bytes_per_cta = (int32_t)c->smem;
+  out->warps_per_cta = c->warps_per_cta;
+  out->ctas = c->ctas;
+  out->slot_capacity = c->slot_cap;
+  if (c->ev_valid && !c->in_sweep) {
+    float t01 = 0, t12 = 0, t23 = 0;
+    CU(cudaEventElapsedTime(&t01, c->ev[0], c->ev[1]));
+    CU(cudaEventElapsedTime(&t12, c->ev[1], c->ev[2]));
+    CU(cudaEventElapsedTime(&t23, c->ev[2], c->ev[3]));
+    out->last_tables_ms = t01;
+    out->last_sample_ms = t12;
+    out->last_finish_ms = t23;
+    out->last_sweep_ms = (double)t01 + t12 + t23;
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out->tokens_moved_last = (int64_t)h[1];
+    out->prior_bucket_last = (int64_t)h[2];
+    out->mean_doc_topics = c->N > 0 ? (double)h[3] / (double)c->N : 0.0;
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_host_alloc(void** out, size_t bytes) {
+  if (!out) return fail(B200LDA_EINVAL, "null argument");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200LDA_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_host_free(void* p) {
+  if (!p) return B200LDA_OK;
+  if (cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(B200LDA_ECUDA, "cudaFreeHost failed");
+  }
+  return B200LDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// pack_kernels.cuh — K1: corpus packing and count construction.
+//
+// Replaces ParallelTopicModel.addInstances + buildInitialTypeTopicCounts (reference call sites
+// cmu_ron/TrainAndPredict.java:162,174 and cmu/TrainAndPredict.java:260,271):
+// uniform random initial topics, n_wk / n_k histograms and the sparse per-document topic rows.
+// Mallet keeps int[L_d] topics + packed int rows on the Java heap; here z is uint16, n_wk a dense
+// int32 V x K matrix (row = word, so one word's topics are contiguous for the sampler's gathers)
+// and n_dk one packed (topic<<16 | count) row per document with ascending topics.
+#pragma once
+#include "device_common.cuh"
+
+namespace b200lda {
+
+// z[i] = floor(K * x / 2^32), x = Philox(seed; global token, sweep 0, stream 1).x
+__global__ void k_init_z(int64_t N, int K, uint64_t seed, int64_t global_off, uint16_t* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const uint32_t x = token_random(seed, (uint64_t)(global_off + i), 0u, 1u).x;
+    z[i] = (uint16_t)(((uint64_t)x * (uint64_t)K) >> 32);
+  }
+}
+
+// int32 host layout -> uint16 device layout; flags out-of-range topics.
+__global__ void k_narrow_z(int64_t N, int K, const int32_t* __restrict__ in, uint16_t* __restrict__ out,
+                           int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int32_t v = in[i];
+    if (v < 0 || v >= K) {
+      *bad = 1;
+      out[i] = 0;
+    } else {
+      out[i] = (uint16_t)v;
+    }
+  }
+}
+
+__global__ void k_widen_z(int64_t N, const uint16_t* __restrict__ in, int32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) out[i] = (int32_t)in[i];
+}
+
+// Validates word ids and histograms them (word -> token CSR, pass 1).
+__global__ void k_word_hist(int64_t N, int V, const int32_t* __restrict__ tok_word,
+                            unsigned long long* __restrict__ word_count, int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int32_t w = tok_word[i];
+    if (w < 0 || w >= V) {
+      *bad = 1;
+    } else {
+      atomicAdd(word_count + w, 1ull);
+    }
+  }
+}
+
+// Single-block exclusive scan of word_count into word_ptr[V+1] (V is at most a few million).
+__global__ void k_exclusive_scan_u64(int n, const unsigned long long* __restrict__ in,
+                                     long long* __restrict__ out) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    unsigned long long v = (i < n) ? in[i] : 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(kFullMask, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long t = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0ull;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFullMask, t, d);
+        if (lane >= d) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const unsigned long long warp_off = warp ? s_warp[warp - 1] : 0ull;
+    const unsigned long long carry = s_carry;
+    if (i < n) out[i] = (long long)(carry + warp_off + x - v);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = (long long)s_carry;
+}
+
+// word -> token CSR, pass 2: wtok[word_ptr[w] + r] = token index; order inside a word is by
+// cursor arrival (any order is a valid CSR; the counts built from it are order-independent).
+__global__ void k_word_scatter(int64_t N, const int32_t* __restrict__ tok_word, const long long* __restrict__ word_ptr,
+                               unsigned long long* __restrict__ cursor, int64_t* __restrict__ wtok) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int32_t w = tok_word[i];
+    const unsigned long long r = atomicAdd(cursor + w, 1ull);
+    wtok[word_ptr[w] + (long long)r] = i;
+  }
+}
+
+// n_wk rows from the word -> token order: one warp per word gathers its tokens' topics and
+// accumulates the row with shared-memory-free integer atomics on its own (L2-resident) row.
+__global__ void __launch_bounds__(256)
+k_count_by_word(int V, int K, const long long* __restrict__ word_ptr, const int64_t* __restrict__ wtok,
+                const uint16_t* __restrict__ z, int32_t* __restrict__ nwk, int32_t* __restrict__ nk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = gw; w < V; w += nw) {
+    const long long b = word_ptr[w], e = word_ptr[w + 1];
+    int32_t* row = nwk + (size_t)w * K;
+    for (long long i = b + lane; i < e; i += 32) {
+      const int k = (int)z[wtok[i]];
+      atomicAdd(row + k, 1);
+      atomicAdd(nk + k, 1);
+    }
+  }
+}
+
+// Sparse document rows: per warp a dense K-entry histogram (shared memory when it fits, else a
+// per-warp global scratch row), filled from the document's topics, then compacted in ascending
+// topic order with ballot/popc and cleared again.
+__global__ void __launch_bounds__(256)
+k_build_doc_rows(int64_t D, int K, const int64_t* __restrict__ doc_ptr, const uint16_t* __restrict__ z,
+                 const int64_t* __restrict__ row_ptr, int32_t* __restrict__ row_nnz, uint32_t* __restrict__ rows,
+                 uint32_t* __restrict__ scratch /* nullptr => shared memory */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  uint32_t* hist = scratch ? scratch + (size_t)gw * K : reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * K;
+  for (int k = lane; k < K; k += 32) hist[k] = 0u;
+  __syncwarp();
+  for (int64_t d = gw; d < D; d += nw) {
+    const int64_t tb = doc_ptr[d], te = doc_ptr[d + 1];
+    for (int64_t i = tb + lane; i < te; i += 32) atomicAdd(hist + z[i], 1u);
+    __syncwarp();
+    const int64_t rp = row_ptr[d];
+    int n = 0;
+    for (int base = 0; base < K; base += 32) {
+      const int k = base + lane;
+      const uint32_t c = (k < K) ? hist[k] : 0u;
+      const unsigned m = __ballot_sync(kFullMask, c != 0u);
+      if (c != 0u) {
+        rows[rp + n + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)k << 16) | c;
+        hist[k] = 0u;
+      }
+      n += __popc(m);
+    }
+    if (lane == 0) row_nnz[d] = n;
+    __syncwarp();
+  }
+}
+
+}  // namespace b200lda

@@ -1,0 +1,107 @@
+// table_kernels.cuh — K2 (per-sweep tables) and K4 (AD-LDA delta / apply).
+//
+// K2 replaces the smoothingOnlyMass / cachedCoefficients set-up at the top of Mallet's
+// WorkerRunnable.run (reached through estimate(), reference cmu_ron/TrainAndPredict.java:166):
+// everything about the conditional that does not depend on the document is folded, once per
+// sweep, into  invden_k = 1/(n_k + V beta),  ab_k = alpha_k * invden_k  and, per word, the
+// inclusive prefix table of  (n_wk + beta) * ab_k  with its fan-out-32 search levels.
+// K4 replaces ParallelTopicModel.sumTypeTopicCounts + the copy-back into every worker replica
+// (setNumThreads(4), reference cmu_ron/TrainAndPredict.java:164, cmu/TrainAndPredict.java:262):
+// each shard forms delta = counts_after - counts_before, the caller all-reduces it, and every
+// shard applies the sum.
+#pragma once
+#include "device_common.cuh"
+
+namespace b200lda {
+
+__global__ void k_topic_tables(int K, const int32_t* __restrict__ nk, const float* __restrict__ alpha_f,
+                               float vbeta, float* __restrict__ invden, float* __restrict__ ab) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float inv = __fdiv_rn(1.0f, fadd((float)nk[k], vbeta));
+  invden[k] = inv;
+  ab[k] = fmul(alpha_f[k], inv);
+}
+
+// One warp per word (grid-stride): coalesced 128-byte reads of the n_wk row, tile scan, coalesced
+// writes of the prefix row, then the upper search levels by sub-sampling the level below.
+__global__ void __launch_bounds__(256)
+k_prior_rows(int V, int K, const int32_t* __restrict__ nwk, const float* __restrict__ ab, float beta_f,
+             PriorLayout L, float* __restrict__ prior, float* __restrict__ q) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * warps_per_block;
+  for (int64_t w = gw; w < V; w += nw) {
+    const int32_t* row = nwk + (size_t)w * K;
+    float* out = prior + (size_t)w * L.stride;
+    float carry = 0.0f;
+    for (int base = 0; base < K; base += 32) {
+      const int k = base + lane;
+      float b = 0.0f;
+      if (k < K) b = fmul(fadd((float)row[k], beta_f), __ldg(ab + k));
+      b = warp_scan_inclusive(b, lane);
+      const float P = fadd(carry, b);
+      if (k < K) out[L.off[0] + k] = P;
+      carry = __shfl_sync(kFullMask, P, 31);
+    }
+    __syncwarp();
+    for (int lev = 1; lev < L.nlev; ++lev) {
+      const float* lower = out + L.off[lev - 1];
+      float* upper = out + L.off[lev];
+      const int nl = L.size[lev - 1];
+      for (int m = lane; m < L.size[lev]; m += 32) upper[m] = lower[min(32 * m + 31, nl - 1)];
+      __syncwarp();
+    }
+    if (lane == 0) q[w] = out[L.off[0] + K - 1];
+  }
+}
+
+// nk += nk_delta; nk_delta = 0   (single-shard sweep finish)
+__global__ void k_apply_nk(int K, int32_t* __restrict__ nk, int32_t* __restrict__ nk_delta) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  nk[k] += nk_delta[k];
+  nk_delta[k] = 0;
+}
+
+// exchange[i] = after[i] - before[i]  (i < VK),  exchange[VK + k] = nk_delta[k]
+__global__ void k_form_delta(size_t VK, int K, const int32_t* __restrict__ after,
+                             const int32_t* __restrict__ before, const int32_t* __restrict__ nk_delta,
+                             int32_t* __restrict__ exchange) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = VK >> 2;
+  const int4* a4 = reinterpret_cast<const int4*>(after);
+  const int4* b4 = reinterpret_cast<const int4*>(before);
+  int4* e4 = reinterpret_cast<int4*>(exchange);
+  for (size_t i = tid; i < n4; i += stride) {
+    const int4 a = a4[i], b = b4[i];
+    e4[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+  }
+  for (size_t i = (n4 << 2) + tid; i < VK; i += stride) exchange[i] = after[i] - before[i];
+  for (size_t k = tid; k < (size_t)K; k += stride) exchange[VK + k] = nk_delta[k];
+}
+
+// nwk[i] = before[i] + exchange[i];  nk[k] += exchange[VK + k];  nk_delta = 0
+__global__ void k_apply_delta(size_t VK, int K, int32_t* __restrict__ nwk, const int32_t* __restrict__ before,
+                              const int32_t* __restrict__ exchange, int32_t* __restrict__ nk,
+                              int32_t* __restrict__ nk_delta) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = VK >> 2;
+  const int4* b4 = reinterpret_cast<const int4*>(before);
+  const int4* e4 = reinterpret_cast<const int4*>(exchange);
+  int4* o4 = reinterpret_cast<int4*>(nwk);
+  for (size_t i = tid; i < n4; i += stride) {
+    const int4 b = b4[i], e = e4[i];
+    o4[i] = make_int4(b.x + e.x, b.y + e.y, b.z + e.z, b.w + e.w);
+  }
+  for (size_t i = (n4 << 2) + tid; i < VK; i += stride) nwk[i] = before[i] + exchange[i];
+  for (size_t k = tid; k < (size_t)K; k += stride) {
+    nk[k] += exchange[VK + k];
+    nk_delta[k] = 0;
+  }
+}
+
+}  // namespace b200lda

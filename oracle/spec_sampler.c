@@ -1,0 +1,415 @@
+/*
+ * oracle/spec_sampler.c — TEST INFRASTRUCTURE (CPU oracle, part b). PARITY UNPINNED (see
+ * lda_oracle.h). Never linked into or called from the product library.
+ *
+ * Sequential restatement of the sampling spec the sm_100a kernels implement (DESIGN.md
+ * "sampling spec"): the collapsed conditional
+ *      p(z=k) ∝ (n_wk^{-i} + β)(n_dk^{-i} + α_k) / (n_k + Vβ)
+ * that Mallet's WorkerRunnable.sampleTopicsForOneDoc evaluates (reference call sites
+ * cmu_ron/TrainAndPredict.java:166, cmu/TrainAndPredict.java:265), split in
+ * a sparse doc bucket  n_dk (n_wk+β)/(n_k+Vβ)  and a per-word prior bucket  α_k (n_wk+β)/(n_k+Vβ),
+ * all in fp32 with every operation individually rounded (compile with -ffp-contract=off) and all
+ * prefix sums in the 32-lane Kogge-Stone + sequential-carry order a warp produces.
+ * Same counts + same uniforms  =>  same topic index as the GPU, bit for bit.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lda_oracle.h"
+#include "philox.h"
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32_10(ctr, key, out);
+}
+
+void oracle_init_z_philox(int64_t N, int32_t K, uint64_t seed, int64_t global_off, int32_t* z) {
+  for (int64_t i = 0; i < N; ++i) {
+    uint32_t r[4];
+    b200lda_token_random(seed, (uint64_t)(global_off + i), 0u, 1u, r);
+    z[i] = (int32_t)(((uint64_t)r[0] * (uint64_t)K) >> 32);
+  }
+}
+
+void oracle_count(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr, const int32_t* tok_word,
+                  const int32_t* z, int32_t* nwk, int32_t* nk) {
+  memset(nwk, 0, sizeof(int32_t) * (size_t)V * (size_t)K);
+  memset(nk, 0, sizeof(int32_t) * (size_t)K);
+  int64_t N = doc_ptr[D];
+  for (int64_t i = 0; i < N; ++i) {
+    nwk[(size_t)tok_word[i] * K + z[i]]++;
+    nk[z[i]]++;
+  }
+}
+
+void oracle_ndk_csr(int64_t D, int32_t K, const int64_t* doc_ptr, const int32_t* z,
+                    int64_t* row_ptr, int32_t* nnz, int32_t* topic, int32_t* count) {
+  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+  int64_t off = 0;
+  for (int64_t d = 0; d < D; ++d) {
+    int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    row_ptr[d] = off;
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
+    int32_t n = 0;
+    for (int32_t k = 0; k < K; ++k)
+      if (dense[k]) {
+        topic[off + n] = k;
+        count[off + n] = dense[k];
+        dense[k] = 0;
+        ++n;
+      }
+    nnz[d] = n;
+    off += (len < K) ? len : K;
+  }
+  row_ptr[D] = off;
+  free(dense);
+}
+
+void oracle_tile_scan_f32(const float* in, int64_t n, float* out) {
+  float carry = 0.0f;
+  for (int64_t base = 0; base < n; base += 32) {
+    float x[32], y[32];
+    for (int l = 0; l < 32; ++l) x[l] = (base + l < n) ? in[base + l] : 0.0f;
+    for (int d = 1; d < 32; d <<= 1) {
+      for (int l = 0; l < 32; ++l) y[l] = (l >= d) ? (x[l] + x[l - d]) : x[l];
+      memcpy(x, y, sizeof(x));
+    }
+    for (int l = 0; l < 32 && base + l < n; ++l) out[base + l] = carry + x[l];
+    carry = carry + x[31];
+  }
+}
+
+void oracle_spec_tables(int32_t V, int32_t K, const int32_t* nwk, const int32_t* nk,
+                        const double* alpha, double beta, float* invden, float* ab, float* prior,
+                        float* q) {
+  const float beta_f = (float)beta;
+  const float vbeta = (float)V * beta_f;
+  for (int32_t k = 0; k < K; ++k) {
+    invden[k] = 1.0f / ((float)nk[k] + vbeta);
+    ab[k] = (float)alpha[k] * invden[k];
+  }
+  float* b = (float*)malloc(sizeof(float) * (size_t)K);
+  for (int32_t w = 0; w < V; ++w) {
+    const int32_t* row = nwk + (size_t)w * K;
+    for (int32_t k = 0; k < K; ++k) b[k] = ((float)row[k] + beta_f) * ab[k];
+    oracle_tile_scan_f32(b, K, prior + (size_t)w * K);
+    q[w] = prior[(size_t)w * K + K - 1];
+  }
+  free(b);
+}
+
+/* Levels: L0 = row (size K); L(i+1)[m] = L(i)[min(32m+31, size_i-1)]; top level has <= 32
+ * entries. Search picks, top-down, the first entry > s inside the current 32-block, or the
+ * block's last entry when none is. */
+int32_t oracle_spec_hsearch(const float* row, int32_t K, float s) {
+  int32_t sizes[8];
+  int nl = 0;
+  sizes[nl++] = K;
+  while (sizes[nl - 1] > 32) {
+    sizes[nl] = (sizes[nl - 1] + 31) / 32;
+    ++nl;
+  }
+  int32_t block = 0; /* index of the 32-block inside the current level */
+  for (int lev = nl - 1; lev >= 0; --lev) {
+    int32_t lo = block * 32;
+    int32_t hi = lo + 32;
+    if (hi > sizes[lev]) hi = sizes[lev];
+    int32_t pick = hi - 1;
+    for (int32_t m = lo; m < hi; ++m) {
+      /* value of level-`lev` entry m = fine entry min((m+1)*32^lev - 1, K-1) */
+      int64_t fine = (int64_t)(m + 1);
+      for (int t = 0; t < lev; ++t) fine *= 32;
+      fine -= 1;
+      if (fine > K - 1) fine = K - 1;
+      if (row[fine] > s) {
+        pick = m;
+        break;
+      }
+    }
+    block = pick;
+  }
+  return block;
+}
+
+int32_t oracle_spec_select(int32_t K, const int32_t* slot_topic, const int32_t* slot_count,
+                           int32_t nslots, const int32_t* nwk_row, const float* invden,
+                           const float* ab, const float* prior_row, float q_w, float beta_f,
+                           int32_t old_topic, float u) {
+  /* doc bucket weights, own token excluded from n_wk and n_dk */
+  float stack_a[256] = {0.0f}, stack_s[256];
+  float* a = nslots <= 256 ? stack_a : (float*)malloc(sizeof(float) * (size_t)nslots);
+  float* S = nslots <= 256 ? stack_s : (float*)malloc(sizeof(float) * (size_t)nslots);
+  for (int32_t j = 0; j < nslots; ++j) {
+    int32_t t = slot_topic[j];
+    int32_t c = slot_count[j];
+    int32_t n = nwk_row[t];
+    if (t == old_topic) {
+      c -= 1;
+      n -= 1;
+      if (n < 0) n = 0;
+    }
+    float x = (float)n + beta_f;
+    float y = x * invden[t];
+    a[j] = y * (float)c;
+  }
+  oracle_tile_scan_f32(a, nslots, S);
+  const float A = nslots > 0 ? S[nslots - 1] : 0.0f;
+  const float delta = ab[old_topic];
+  float qp = q_w - delta;
+  if (qp < 0.0f) qp = 0.0f;
+  const float T = A + qp;
+  const float x = u * T;
+  int32_t result;
+  if (x < A) {
+    int32_t j = nslots - 1;
+    for (int32_t i = 0; i < nslots; ++i)
+      if (S[i] > x) {
+        j = i;
+        break;
+      }
+    result = slot_topic[j];
+  } else {
+    const float y = x - A;
+    const float po = prior_row[old_topic];
+    const float pod = po - delta;
+    const float s = (y < pod) ? y : (y + delta);
+    result = oracle_spec_hsearch(prior_row, K, s);
+  }
+  if (a != stack_a) free(a);
+  if (S != stack_s) free(S);
+  return result;
+}
+
+/* ---- drivers ---------------------------------------------------------------------------- */
+
+typedef struct {
+  float *invden, *ab, *prior, *q;
+} spec_tables;
+
+static spec_tables tables_alloc(int32_t V, int32_t K) {
+  spec_tables t;
+  t.invden = (float*)malloc(sizeof(float) * (size_t)K);
+  t.ab = (float*)malloc(sizeof(float) * (size_t)K);
+  t.prior = (float*)malloc(sizeof(float) * (size_t)V * (size_t)K);
+  t.q = (float*)malloc(sizeof(float) * (size_t)V);
+  return t;
+}
+static void tables_free(spec_tables* t) {
+  free(t->invden);
+  free(t->ab);
+  free(t->prior);
+  free(t->q);
+}
+
+static float token_uniform(uint64_t seed, int64_t g, uint32_t sweep) {
+  uint32_t r[4];
+  b200lda_token_random(seed, (uint64_t)g, sweep, 0u, r);
+  return b200lda_u24(r[0]);
+}
+
+void oracle_spec_frozen(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                        const int32_t* tok_word, const int32_t* z_in, const double* alpha,
+                        double beta, uint64_t seed, uint32_t sweep, int64_t global_off,
+                        const float* uniforms, int32_t* z_out) {
+  int32_t* nwk = (int32_t*)malloc(sizeof(int32_t) * (size_t)V * (size_t)K);
+  int32_t* nk = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  oracle_count(D, V, K, doc_ptr, tok_word, z_in, nwk, nk);
+  spec_tables t = tables_alloc(V, K);
+  oracle_spec_tables(V, K, nwk, nk, alpha, beta, t.invden, t.ab, t.prior, t.q);
+  const float beta_f = (float)beta;
+  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+  int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  for (int64_t d = 0; d < D; ++d) {
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z_in[i]]++;
+    int32_t ns = 0;
+    for (int32_t k = 0; k < K; ++k)
+      if (dense[k]) {
+        st[ns] = k;
+        sc[ns] = dense[k];
+        dense[k] = 0;
+        ++ns;
+      }
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
+      int32_t w = tok_word[i];
+      float u = uniforms ? uniforms[i] : token_uniform(seed, global_off + i, sweep);
+      z_out[i] = oracle_spec_select(K, st, sc, ns, nwk + (size_t)w * K, t.invden, t.ab,
+                                    t.prior + (size_t)w * K, t.q[w], beta_f, z_in[i], u);
+    }
+  }
+  free(dense);
+  free(st);
+  free(sc);
+  tables_free(&t);
+  free(nwk);
+  free(nk);
+}
+
+void oracle_spec_sweeps(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                        const int32_t* tok_word, int32_t* z, const double* alpha, double beta,
+                        uint64_t seed, uint32_t first_sweep, int32_t n_sweeps, int64_t global_off) {
+  oracle_spec_sweeps_mode(D, V, K, doc_ptr, tok_word, z, alpha, beta, seed, first_sweep, n_sweeps,
+                          global_off, 0);
+}
+
+/* live != 0: n_wk moves immediately (a sequential rendering of the GPU's LIVE mode: the prior
+ * table and n_k still date from the sweep start). live == 0: DEFERRED mode. */
+void oracle_spec_sweeps_mode(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                             const int32_t* tok_word, int32_t* z, const double* alpha, double beta,
+                             uint64_t seed, uint32_t first_sweep, int32_t n_sweeps,
+                             int64_t global_off, int32_t live) {
+  int32_t* nwk = (int32_t*)malloc(sizeof(int32_t) * (size_t)V * (size_t)K);
+  int32_t* nk = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  spec_tables t = tables_alloc(V, K);
+  const float beta_f = (float)beta;
+  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+  int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  for (int32_t it = 0; it < n_sweeps; ++it) {
+    const uint32_t sweep = first_sweep + (uint32_t)it;
+    /* frozen per-sweep snapshot: recounting from z == applying the summed deltas */
+    oracle_count(D, V, K, doc_ptr, tok_word, z, nwk, nk);
+    oracle_spec_tables(V, K, nwk, nk, alpha, beta, t.invden, t.ab, t.prior, t.q);
+    for (int64_t d = 0; d < D; ++d) {
+      for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
+      int32_t ns = 0;
+      for (int32_t k = 0; k < K; ++k)
+        if (dense[k]) {
+          st[ns] = k;
+          sc[ns] = dense[k];
+          dense[k] = 0;
+          ++ns;
+        }
+      for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
+        const int32_t w = tok_word[i];
+        const int32_t o = z[i];
+        const float u = token_uniform(seed, global_off + i, sweep);
+        const int32_t n = oracle_spec_select(K, st, sc, ns, nwk + (size_t)w * K, t.invden, t.ab,
+                                             t.prior + (size_t)w * K, t.q[w], beta_f, o, u);
+        if (n != o) {
+          /* remove one from o (delete slot if it empties), add one to n (sorted insert) */
+          int32_t jo = 0;
+          while (st[jo] != o) ++jo;
+          if (--sc[jo] == 0) {
+            memmove(st + jo, st + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
+            memmove(sc + jo, sc + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
+            --ns;
+          }
+          int32_t jn = 0;
+          while (jn < ns && st[jn] < n) ++jn;
+          if (jn < ns && st[jn] == n) {
+            sc[jn]++;
+          } else {
+            memmove(st + jn + 1, st + jn, sizeof(int32_t) * (size_t)(ns - jn));
+            memmove(sc + jn + 1, sc + jn, sizeof(int32_t) * (size_t)(ns - jn));
+            st[jn] = n;
+            sc[jn] = 1;
+            ++ns;
+          }
+          z[i] = n;
+          if (live) {
+            nwk[(size_t)w * K + o]--;
+            nwk[(size_t)w * K + n]++;
+          }
+        }
+      }
+    }
+  }
+  free(dense);
+  free(st);
+  free(sc);
+  tables_free(&t);
+  free(nwk);
+  free(nk);
+}
+
+void oracle_exact_conditional(int32_t K, int32_t V, const int32_t* ndk_dense,
+                              const int32_t* nwk_row, const int32_t* nk, const double* alpha,
+                              double beta, int32_t old_topic, double* p) {
+  double tot = 0.0;
+  for (int32_t k = 0; k < K; ++k) {
+    int32_t ex = (k == old_topic) ? 1 : 0;
+    double v = ((double)(nwk_row[k] - ex) + beta) * ((double)(ndk_dense[k] - ex) + alpha[k]) /
+               ((double)nk[k] + (double)V * beta);
+    p[k] = v;
+    tot += v;
+  }
+  for (int32_t k = 0; k < K; ++k) p[k] /= tot;
+}
+
+/* ---- log-likelihood, theta, phi ----------------------------------------------------------- */
+
+double oracle_log_gamma_stirling(double z) {
+  int shift = 0;
+  while (z < 2.0) {
+    z += 1.0;
+    shift++;
+  }
+  const double half_log_2pi = 0.91893853320467274178;
+  double result = half_log_2pi + (z - 0.5) * log(z) - z + 1.0 / (12.0 * z) -
+                  1.0 / (360.0 * z * z * z) + 1.0 / (1260.0 * z * z * z * z * z);
+  while (shift > 0) {
+    shift--;
+    z -= 1.0;
+    result -= log(z);
+  }
+  return result;
+}
+
+double oracle_loglik(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                     const int32_t* tok_word, const int32_t* z, const double* alpha, double beta,
+                     int32_t stirling) {
+  double (*lg)(double) = stirling ? oracle_log_gamma_stirling : lgamma;
+  double alpha_sum = 0.0;
+  for (int32_t k = 0; k < K; ++k) alpha_sum += alpha[k];
+  double* lg_alpha = (double*)malloc(sizeof(double) * (size_t)K);
+  for (int32_t k = 0; k < K; ++k) lg_alpha[k] = lg(alpha[k]);
+  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+  double ll = 0.0;
+  for (int64_t d = 0; d < D; ++d) {
+    int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
+    for (int32_t k = 0; k < K; ++k)
+      if (dense[k] > 0) {
+        ll += lg(alpha[k] + (double)dense[k]) - lg_alpha[k];
+        dense[k] = 0;
+      }
+    ll -= lg(alpha_sum + (double)len);
+  }
+  ll += (double)D * lg(alpha_sum);
+  int32_t* nwk = (int32_t*)malloc(sizeof(int32_t) * (size_t)V * (size_t)K);
+  int32_t* nk = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  oracle_count(D, V, K, doc_ptr, tok_word, z, nwk, nk);
+  int64_t nonzero = 0;
+  for (size_t i = 0; i < (size_t)V * (size_t)K; ++i)
+    if (nwk[i] > 0) {
+      ++nonzero;
+      ll += lg(beta + (double)nwk[i]);
+    }
+  for (int32_t k = 0; k < K; ++k) ll -= lg(beta * (double)V + (double)nk[k]);
+  ll += (double)K * lg(beta * (double)V);
+  ll -= (double)nonzero * lg(beta);
+  free(nwk);
+  free(nk);
+  free(dense);
+  free(lg_alpha);
+  return ll;
+}
+
+void oracle_theta(int32_t K, const int32_t* z_doc, int64_t len, const double* alpha, double* out) {
+  double alpha_sum = 0.0;
+  for (int32_t k = 0; k < K; ++k) {
+    alpha_sum += alpha[k];
+    out[k] = 0.0;
+  }
+  for (int64_t i = 0; i < len; ++i) out[z_doc[i]] += 1.0;
+  for (int32_t k = 0; k < K; ++k) out[k] = (out[k] + alpha[k]) / ((double)len + alpha_sum);
+}
+
+void oracle_phi(int32_t V, int32_t K, const int32_t* nwk, const int32_t* nk, double beta,
+                double* out) {
+  for (int32_t k = 0; k < K; ++k)
+    for (int32_t w = 0; w < V; ++w)
+      out[(size_t)k * V + w] =
+          ((double)nwk[(size_t)w * K + k] + beta) / ((double)nk[k] + (double)V * beta);
+}

@@ -1,0 +1,166 @@
+"""GPU parity tests proper: the CUDA path, through the C ABI, against the CPU oracle.
+
+Bit-exact (integer / index work): initial topics, n_wk / n_k / n_dk, the frozen-snapshot topic
+index of every token, and the whole DEFERRED-mode chain. Floating point: log-likelihood within
+1e-9 relative of the oracle's fp64 evaluation of the same counts.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALPHA, BETA = 0.1, 0.01
+
+
+def _sampler(K, V, seed, mode=None, **kw):
+    import ldagibbssampling_b200 as L
+    return L.Sampler(K, V, ALPHA * K, BETA, seed=seed,
+                     mode=L.MODE_DEFERRED if mode is None else mode, **kw)
+
+
+CASES = [
+    # D, V, mean_len, k_true, K
+    (300, 200, 40.0, 8, 4),
+    (300, 500, 60.0, 10, 20),
+    (200, 400, 120.0, 20, 100),
+    (150, 300, 200.0, 30, 1000),
+    (60, 100, 300.0, 10, 1500),
+]
+
+
+@pytest.mark.parametrize("D,V,mean_len,k_true,K", CASES)
+def test_init_and_counts_match_oracle(oracle, D, V, mean_len, k_true, K):
+    dp, tok = oracle.gen_corpus(D, V, mean_len, k_true, 11)
+    s = _sampler(K, V, seed=5)
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    z = s.assignments()
+    assert np.array_equal(z, oracle.init_z(len(tok), K, 5))
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    assert np.array_equal(s.nwk(), nwk)
+    assert np.array_equal(s.nk(), nk)
+    rp, nnz, topic, cnt = oracle.ndk_csr(dp, z, K)
+    g_rp, g_topic, g_cnt = s.ndk_csr()
+    assert np.array_equal(np.diff(g_rp), nnz)
+    for d in range(D):
+        assert np.array_equal(g_topic[g_rp[d]:g_rp[d + 1]], topic[rp[d]:rp[d] + nnz[d]])
+        assert np.array_equal(g_cnt[g_rp[d]:g_rp[d + 1]], cnt[rp[d]:rp[d] + nnz[d]])
+
+
+@pytest.mark.parametrize("D,V,mean_len,k_true,K", CASES)
+def test_frozen_snapshot_index_parity(oracle, D, V, mean_len, k_true, K):
+    dp, tok = oracle.gen_corpus(D, V, mean_len, k_true, 12)
+    z0 = oracle.init_z(len(tok), K, 9)
+    s = _sampler(K, V, seed=9)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    # Philox uniforms
+    got = s.sample_frozen(None, sweep=3)
+    want = oracle.spec_frozen(dp, tok, z0, V, K, ALPHA, BETA, 9, 3)
+    assert np.array_equal(got, want)
+    # caller-supplied uniforms
+    u = np.random.default_rng(0).random(len(tok), dtype=np.float32)
+    got = s.sample_frozen(u)
+    want = oracle.spec_frozen(dp, tok, z0, V, K, ALPHA, BETA, 9, 1, uniforms=u)
+    assert np.array_equal(got, want)
+    # frozen mode moved nothing
+    assert np.array_equal(s.assignments(), z0)
+
+
+@pytest.mark.parametrize("D,V,mean_len,k_true,K", CASES[:4])
+def test_deferred_chain_bit_exact(oracle, D, V, mean_len, k_true, K):
+    dp, tok = oracle.gen_corpus(D, V, mean_len, k_true, 13)
+    z0 = oracle.init_z(len(tok), K, 21)
+    s = _sampler(K, V, seed=21)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    s.sweep(4)
+    want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 21, 1, 4)
+    got = s.assignments()
+    assert np.array_equal(got, want)
+    nwk, nk = oracle.count(dp, tok, want, V, K)
+    assert np.array_equal(s.nwk(), nwk)
+    assert np.array_equal(s.nk(), nk)
+
+
+@pytest.mark.parametrize("mode_name", ["LIVE", "DEFERRED"])
+def test_count_invariants_after_sweeps(oracle, mode_name):
+    import ldagibbssampling_b200 as L
+    D, V, K = 2000, 1500, 50
+    dp, tok = oracle.gen_corpus(D, V, 80.0, 20, 14)
+    s = _sampler(K, V, seed=3, mode=getattr(L, "MODE_" + mode_name))
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    for _ in range(3):
+        s.sweep(2)
+        z = s.assignments()
+        nwk, nk = oracle.count(dp, tok, z, V, K)
+        g_nwk, g_nk = s.nwk(), s.nk()
+        assert np.array_equal(g_nwk, nwk)
+        assert np.array_equal(g_nk, nk)
+        assert g_nwk.sum() == g_nk.sum() == len(tok)
+        rp, topic, cnt = s.ndk_csr()
+        assert cnt.sum() == len(tok)
+        o_rp, o_nnz, o_topic, o_cnt = oracle.ndk_csr(dp, z, K)
+        assert np.array_equal(np.diff(rp), o_nnz)
+        d = D // 2
+        assert np.array_equal(topic[rp[d]:rp[d + 1]], o_topic[o_rp[d]:o_rp[d] + o_nnz[d]])
+        assert np.array_equal(cnt[rp[d]:rp[d + 1]], o_cnt[o_rp[d]:o_rp[d] + o_nnz[d]])
+
+
+def test_loglik_theta_phi_match_oracle(oracle):
+    D, V, K = 500, 800, 30
+    dp, tok = oracle.gen_corpus(D, V, 70.0, 12, 15)
+    s = _sampler(K, V, seed=4)
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    s.sweep(3)
+    z = s.assignments()
+    want = oracle.loglik(dp, tok, z, V, K, ALPHA, BETA)
+    got = s.loglik()
+    assert abs(got - want) <= 1e-9 * abs(want)  # fp64, tolerance 1e-9 relative
+    stirling = oracle.loglik(dp, tok, z, V, K, ALPHA, BETA, stirling=True)
+    assert abs(got - stirling) <= 1e-7 * abs(stirling)  # Mallet's logGammaStirling
+    th = s.theta(0, D)
+    for d in (0, 7, D - 1):
+        assert np.allclose(th[d], oracle.theta(z[dp[d]:dp[d + 1]], K, ALPHA), rtol=1e-14, atol=0)
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    assert np.allclose(s.phi(), oracle.phi(nwk, nk, BETA), rtol=1e-14, atol=0)
+
+
+def test_empty_and_ragged_documents(oracle):
+    K, V = 16, 40
+    lens = np.array([0, 1, 0, 0, 33, 1, 64, 0, 2, 700, 0], np.int64)
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rng = np.random.default_rng(3)
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z0 = oracle.init_z(len(tok), K, 2)
+    s = _sampler(K, V, seed=2)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    assert np.array_equal(s.sample_frozen(None, 1), oracle.spec_frozen(dp, tok, z0, V, K, ALPHA, BETA, 2, 1))
+    s.sweep(3)
+    assert np.array_equal(s.assignments(), oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 2, 1, 3))
+    # a corpus with no tokens at all
+    s2 = _sampler(K, V, seed=2)
+    s2.load_corpus(np.zeros(4, np.int64), np.zeros(0, np.int32))
+    s2.init_assignments(None)
+    s2.sweep(1)
+    assert s2.nk().sum() == 0
+
+
+def test_errors_are_reported_not_swallowed(oracle):
+    import ldagibbssampling_b200 as L
+    s = _sampler(8, 10, seed=1)
+    with pytest.raises(L.B200LDAError) as e:
+        s.sweep(1)
+    assert e.value.code == -5  # ESTATE: no corpus
+    with pytest.raises(L.B200LDAError) as e:
+        s.load_corpus(np.array([0, 2], np.int64), np.array([1, 10], np.int32))
+    assert e.value.code == -6  # ERANGE: word id >= V
+    s.load_corpus(np.array([0, 2], np.int64), np.array([1, 9], np.int32))
+    with pytest.raises(L.B200LDAError) as e:
+        s.init_assignments(np.array([0, 8], np.int32))
+    assert e.value.code == -6  # ERANGE: topic >= K
+    with pytest.raises(L.B200LDAError):
+        L.Sampler(0, 10, 1.0, 0.1)
