@@ -92,6 +92,11 @@ typedef struct {
   int64_t prior_bucket_last;      /* tokens resolved through the prior table in the last sweep */
   int64_t device_bytes;           /* device memory held                                       */
   int32_t smem_bytes_per_cta, warps_per_cta, ctas, slot_capacity;
+  /* accumulated since create / b200lda_reset_stats (device times from CUDA events) */
+  int64_t cum_sweeps;
+  double cum_tables_ms, cum_sample_ms, cum_finish_ms;
+  int64_t cum_tokens_moved, cum_prior_bucket;
+  int64_t cum_doc_topics;         /* sum over sampled tokens of the document's non-zero topics */
 } b200lda_stats;
 
 /* Message of the calling thread's most recent failure ("" if none). Never NULL. */
@@ -170,6 +175,7 @@ int b200lda_set_beta(b200lda_ctx* ctx, double beta);
 int b200lda_set_sweep_counter(b200lda_ctx* ctx, int64_t sweeps_done);
 
 int b200lda_get_stats(b200lda_ctx* ctx, b200lda_stats* out);
+int b200lda_reset_stats(b200lda_ctx* ctx);
 
 /* Pinned host staging memory for callers whose runtime cannot pin its own (JVM heaps). */
 int b200lda_host_alloc(void** out, size_t bytes);

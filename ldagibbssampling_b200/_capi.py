@@ -48,6 +48,9 @@ class Stats(C.Structure):
         ("prior_bucket_last", C.c_int64), ("device_bytes", C.c_int64),
         ("smem_bytes_per_cta", C.c_int32), ("warps_per_cta", C.c_int32), ("ctas", C.c_int32),
         ("slot_capacity", C.c_int32),
+        ("cum_sweeps", C.c_int64), ("cum_tables_ms", C.c_double), ("cum_sample_ms", C.c_double),
+        ("cum_finish_ms", C.c_double), ("cum_tokens_moved", C.c_int64),
+        ("cum_prior_bucket", C.c_int64), ("cum_doc_topics", C.c_int64),
     ]
 
     def as_dict(self):
@@ -84,6 +87,7 @@ SYMBOLS = [
     ("b200lda_set_beta", C.c_int, [_P, C.c_double]),
     ("b200lda_set_sweep_counter", C.c_int, [_P, C.c_int64]),
     ("b200lda_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
+    ("b200lda_reset_stats", C.c_int, [_P]),
     ("b200lda_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("b200lda_host_free", C.c_int, [_P]),
 ]
@@ -272,6 +276,9 @@ class Sampler:
         s = Stats()
         self._check(self._lib.b200lda_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def reset_stats(self):
+        self._check(self._lib.b200lda_reset_stats(self._h))
 
 
 def device_count() -> int:

@@ -54,7 +54,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
-constexpr int kStatCounters = 8;  // [0] doc scheduler, [1] moved, [2] prior draws, [3] nnz sum, [4] nnz(n_wk)
+// [0] doc scheduler, [1..3] last sweep {moved, prior draws, nnz sum}, [4] nnz(n_wk), [5..7] cumulative {same three}
+constexpr int kStatCounters = 8;
+constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 
 int round_up32(int x) { return (x + 31) & ~31; }
 
@@ -128,8 +130,14 @@ struct b200lda_ctx {
   bool corpus_loaded = false, assigned = false, in_sweep = false;
   int64_t sweeps_done = 0, tokens_sampled = 0;
   unsigned long long last_moved = 0, last_prior = 0, last_nnz_sum = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool ev_valid = false;
+  // per-sweep device timing: 4 events per sweep (begin, tables done, sample done, end), resolved
+  // lazily at b200lda_get_stats so no sweep ever synchronises for bookkeeping
+  std::vector<cudaEvent_t> ev_pool;
+  int ev_pending = 0;
+  cudaEvent_t* ev = nullptr;  // the current sweep's quadruple
+  double cum_tables_ms = 0, cum_sample_ms = 0, cum_finish_ms = 0;
+  double last_tables_ms = 0, last_sample_ms = 0, last_finish_ms = 0;
+  int64_t cum_sweeps = 0;
 };
 
 namespace {
@@ -284,6 +292,7 @@ SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_w
   p.global_tok_off = c->cfg.global_token_offset;
   p.doc_counter = c->d_counters + 0;
   p.stats = c->d_counters + 1;
+  p.stats_cum = c->d_counters + 5;
   return p;
 }
 
@@ -296,6 +305,39 @@ int launch_sweep(b200lda_ctx* c, const SweepParams& p) {
     k_gibbs_sweep<MODE, false><<<c->ctas, c->warps_per_cta * 32, c->smem, c->stream>>>(p);
   c->launches += 1;
   CU(cudaGetLastError());
+  return B200LDA_OK;
+}
+
+// Fold every finished sweep's event quadruple into the running sums (stream must be idle).
+int resolve_events(b200lda_ctx* c) {
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->ev_pending; ++i) {
+    cudaEvent_t* e = c->ev_pool.data() + 4 * i;
+    float t01 = 0, t12 = 0, t23 = 0;
+    CU(cudaEventElapsedTime(&t01, e[0], e[1]));
+    CU(cudaEventElapsedTime(&t12, e[1], e[2]));
+    CU(cudaEventElapsedTime(&t23, e[2], e[3]));
+    c->cum_tables_ms += t01;
+    c->cum_sample_ms += t12;
+    c->cum_finish_ms += t23;
+    c->last_tables_ms = t01;
+    c->last_sample_ms = t12;
+    c->last_finish_ms = t23;
+    c->cum_sweeps += 1;
+  }
+  c->ev_pending = 0;
+  return B200LDA_OK;
+}
+
+int next_event_quad(b200lda_ctx* c) {
+  if (c->ev_pending == kEventPool) TRY(resolve_events(c));
+  const size_t need = 4 * (size_t)(c->ev_pending + 1);
+  while (c->ev_pool.size() < need) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    c->ev_pool.push_back(e);
+  }
+  c->ev = c->ev_pool.data() + 4 * c->ev_pending;
   return B200LDA_OK;
 }
 
@@ -374,8 +416,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       return bail(fail(B200LDA_ECUDA, "cudaStreamCreate failed"));
     c->own_stream = true;
   }
-  for (auto& e : c->ev)
-    if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(B200LDA_ECUDA, "cudaEventCreate failed"));
+  c->ev_pool.reserve(4 * kEventPool);
   const size_t VK = (size_t)c->V * c->K;
   const bool multi = cfg->world_size > 1;
   if ((rc = dev_alloc_t(c, &c->d_nwk, VK)) || (rc = dev_alloc_t(c, &c->d_nk, c->K)) ||
@@ -427,7 +468,7 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_partial);
   dev_free(c->d_hist_scratch);
   if (c->d_stage) cudaFree(c->d_stage);
-  for (auto& e : c->ev)
+  for (auto& e : c->ev_pool)
     if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
@@ -576,6 +617,7 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   const bool multi = c->cfg.world_size > 1;
   const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
   const size_t VK = (size_t)c->V * c->K;
+  TRY(next_event_quad(c));
   CU(cudaEventRecord(c->ev[0], c->stream));
   TRY(build_tables(c));
   CU(cudaEventRecord(c->ev[1], c->stream));
@@ -622,7 +664,7 @@ int b200lda_sweep_end(b200lda_ctx* c) {
   c->launches += 1;
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[3], c->stream));
-  c->ev_valid = true;
+  c->ev_pending += 1;
   c->in_sweep = false;
   c->sweeps_done += 1;
   c->tokens_sampled += c->N;
@@ -858,21 +900,34 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->warps_per_cta = c->warps_per_cta;
   out->ctas = c->ctas;
   out->slot_capacity = c->slot_cap;
-  if (c->ev_valid && !c->in_sweep) {
-    float t01 = 0, t12 = 0, t23 = 0;
-    CU(cudaEventElapsedTime(&t01, c->ev[0], c->ev[1]));
-    CU(cudaEventElapsedTime(&t12, c->ev[1], c->ev[2]));
-    CU(cudaEventElapsedTime(&t23, c->ev[2], c->ev[3]));
-    out->last_tables_ms = t01;
-    out->last_sample_ms = t12;
-    out->last_finish_ms = t23;
-    out->last_sweep_ms = (double)t01 + t12 + t23;
-    unsigned long long h[4];
-    CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
-    out->tokens_moved_last = (int64_t)h[1];
-    out->prior_bucket_last = (int64_t)h[2];
-    out->mean_doc_topics = c->N > 0 ? (double)h[3] / (double)c->N : 0.0;
-  }
+  if (c->in_sweep) return B200LDA_OK;  // timings of an open sweep are not resolvable yet
+  TRY(resolve_events(c));
+  out->last_tables_ms = c->last_tables_ms;
+  out->last_sample_ms = c->last_sample_ms;
+  out->last_finish_ms = c->last_finish_ms;
+  out->last_sweep_ms = c->last_tables_ms + c->last_sample_ms + c->last_finish_ms;
+  out->cum_sweeps = c->cum_sweeps;
+  out->cum_tables_ms = c->cum_tables_ms;
+  out->cum_sample_ms = c->cum_sample_ms;
+  out->cum_finish_ms = c->cum_finish_ms;
+  unsigned long long h[kStatCounters];
+  CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+  out->tokens_moved_last = (int64_t)h[1];
+  out->prior_bucket_last = (int64_t)h[2];
+  out->mean_doc_topics = c->N > 0 ? (double)h[3] / (double)c->N : 0.0;
+  out->cum_tokens_moved = (int64_t)h[5];
+  out->cum_prior_bucket = (int64_t)h[6];
+  out->cum_doc_topics = (int64_t)h[7];
+  return B200LDA_OK;
+}
+
+int b200lda_reset_stats(b200lda_ctx* c) {
+  TRY(enter(c));
+  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  TRY(resolve_events(c));
+  c->cum_tables_ms = c->cum_sample_ms = c->cum_finish_ms = 0.0;
+  c->cum_sweeps = 0;
+  CU(cudaMemset(c->d_counters + 5, 0, sizeof(unsigned long long) * 3));
   return B200LDA_OK;
 }
 

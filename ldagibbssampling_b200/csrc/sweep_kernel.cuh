@@ -48,6 +48,7 @@ struct SweepParams {
   int64_t global_tok_off;
   unsigned long long* doc_counter;  // dynamic document scheduler
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
+  unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
 };
 
 constexpr int kDocChunk = 4;
@@ -272,9 +273,18 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
   }
 
   if (lane == 0) {
-    if (st_moved) atomicAdd(p.stats + 0, st_moved);
-    if (st_prior) atomicAdd(p.stats + 1, st_prior);
-    if (st_nnz) atomicAdd(p.stats + 2, st_nnz);
+    if (st_moved) {
+      atomicAdd(p.stats + 0, st_moved);
+      atomicAdd(p.stats_cum + 0, st_moved);
+    }
+    if (st_prior) {
+      atomicAdd(p.stats + 1, st_prior);
+      atomicAdd(p.stats_cum + 1, st_prior);
+    }
+    if (st_nnz) {
+      atomicAdd(p.stats + 2, st_nnz);
+      atomicAdd(p.stats_cum + 2, st_nnz);
+    }
   }
 }
 
