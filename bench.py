@@ -229,7 +229,10 @@ def b200_arm(args):
     gen_s = time.perf_counter() - t0
 
     # ---- sampler on torch's current stream so torch CUDA events bracket its kernels --------------
-    stream = torch.cuda.current_stream(dev)
+    # (a dedicated non-default stream: the legacy default stream has handle 0, which the C ABI
+    # reads as "create a private stream")
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     s = L.Sampler(K, V, ALPHA_K * K, BETA, seed=args.seed,
                   mode=L.MODE_LIVE if args.mode == "live" else L.MODE_DEFERRED, device=local_rank,
                   rank=rank, world_size=world, global_token_offset=shard.token_begin,
@@ -324,7 +327,7 @@ def b200_arm(args):
     s.assignments_raw(h_z.data_ptr())  # current chain state, host side
     fence()
     e2e_times = []
-    for i in range(args.e2e_steps + 1):
+    for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         fence()
         t0 = time.perf_counter()
         s.load_corpus_raw(shard.num_docs, h_doc_ptr.data_ptr(), h_words.data_ptr(), shard.num_tokens)

@@ -55,7 +55,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // [0] doc scheduler, [1..3] last sweep {moved, prior draws, nnz sum}, [4] nnz(n_wk), [5..7] cumulative {same three}
-constexpr int kStatCounters = 8;
+constexpr int kStatCounters = 8;   // (+1: [8] second scheduler counter)
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 
 int round_up32(int x) { return (x + 31) & ~31; }
@@ -81,6 +81,13 @@ PriorLayout make_layout(int K) {
 
 }  // namespace
 
+// Launch shape of the sampling kernel for one document class.
+struct SweepShape {
+  int slot_cap = 32, warps_per_cta = 8, ctas = 0, doc_chunk = 4;
+  size_t smem = 0;
+  bool tables_in_smem = true;
+};
+
 struct b200lda_ctx {
   b200lda_config cfg{};
   int K = 0, V = 0;
@@ -102,6 +109,7 @@ struct b200lda_ctx {
   uint32_t* d_rows = nullptr;
   int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
   std::vector<int64_t> h_doc_ptr, h_row_ptr;
+  std::vector<int32_t> h_doc_order;
   int max_doc_len = 0;
 
   // counts + tables
@@ -121,10 +129,11 @@ struct b200lda_ctx {
   uint32_t* d_hist_scratch = nullptr;
   size_t hist_scratch_bytes = 0;
 
-  // sweep launch shape
-  int slot_cap = 32, warps_per_cta = 8, ctas = 0;
-  size_t smem = 0;
-  bool tables_in_smem = true;
+  // sweep launch shapes, one per document class; doc_order lists the long class first
+  SweepShape shape_short, shape_long;
+  int32_t* d_doc_order = nullptr;
+  int64_t n_long = 0;
+  int small_row = 256;
 
   // state
   bool corpus_loaded = false, assigned = false, in_sweep = false;
@@ -206,51 +215,60 @@ int push_alpha(b200lda_ctx* c) {
   return B200LDA_OK;
 }
 
-template <int MODE, bool TS>
-int set_sweep_attr(size_t smem) {
-  CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int MODE, bool LIVE, bool TS>
+int sweep_occupancy(int threads, size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, LIVE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)kMaxSmemPerCta));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gibbs_sweep<MODE, LIVE, TS>, threads, smem));
   return B200LDA_OK;
 }
 
 // Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
-// of slot_cap entries each. slot_cap = min(K, longest document) rounded to a warp tile.
-int configure_sweep(b200lda_ctx* c) {
-  c->slot_cap = std::max(32, round_up32(std::min(c->K, std::max(1, c->max_doc_len))));
+// of slot_cap entries each.
+int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, SweepShape* out) {
+  SweepShape sh;
+  sh.slot_cap = slot_cap;
+  sh.doc_chunk = doc_chunk;
   const size_t tab = 2 * sizeof(float) * (size_t)c->K;
-  const size_t per_warp = 8 * (size_t)c->slot_cap;
+  const size_t per_warp = 8 * (size_t)slot_cap;
   bool ok = false;
   for (int ts = 1; ts >= 0 && !ok; --ts) {
     for (int wpc = 8; wpc >= 1 && !ok; wpc >>= 1) {
       const size_t need = (ts ? tab : 0) + per_warp * wpc;
       if (need <= kMaxSmemPerCta) {
-        c->tables_in_smem = ts != 0;
-        c->warps_per_cta = wpc;
-        c->smem = need;
+        sh.tables_in_smem = ts != 0;
+        sh.warps_per_cta = wpc;
+        sh.smem = need;
         ok = true;
       }
     }
   }
   if (!ok)
     return fail(B200LDA_ERANGE, "document rows of %d slots do not fit shared memory (K=%d, longest doc=%d)",
-                c->slot_cap, c->K, c->max_doc_len);
-  int occ_u = 0, occ_f = 0;
-  if (c->tables_in_smem) {
-    TRY((set_sweep_attr<MODE_UPDATE, true>(c->smem)));
-    TRY((set_sweep_attr<MODE_FROZEN, true>(c->smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_gibbs_sweep<MODE_UPDATE, true>,
-                                                     c->warps_per_cta * 32, c->smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_gibbs_sweep<MODE_FROZEN, true>,
-                                                     c->warps_per_cta * 32, c->smem));
+                slot_cap, c->K, c->max_doc_len);
+  const int threads = sh.warps_per_cta * 32;
+  int occ[3] = {0, 0, 0};
+  if (sh.tables_in_smem) {
+    TRY((sweep_occupancy<MODE_UPDATE, true, true>(threads, sh.smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, true>(threads, sh.smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, true>(threads, sh.smem, &occ[2])));
   } else {
-    TRY((set_sweep_attr<MODE_UPDATE, false>(c->smem)));
-    TRY((set_sweep_attr<MODE_FROZEN, false>(c->smem)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_gibbs_sweep<MODE_UPDATE, false>,
-                                                     c->warps_per_cta * 32, c->smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_gibbs_sweep<MODE_FROZEN, false>,
-                                                     c->warps_per_cta * 32, c->smem));
+    TRY((sweep_occupancy<MODE_UPDATE, true, false>(threads, sh.smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, false>(threads, sh.smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, false>(threads, sh.smem, &occ[2])));
   }
-  const int occ = std::max(1, std::min(occ_u, occ_f));
-  c->ctas = c->sm_count * occ;  // persistent grid: every CTA resident, documents fetched dynamically
+  const int o = std::max(1, std::min(occ[0], std::min(occ[1], occ[2])));
+  sh.ctas = c->sm_count * o;  // persistent grid: every CTA resident, documents fetched dynamically
+  *out = sh;
+  return B200LDA_OK;
+}
+
+// Two document classes: rows of at most kSmallRow slots (the bulk: small per-warp shared memory,
+// high occupancy) and the long tail (rows up to min(K, longest document)).
+int configure_sweep(b200lda_ctx* c) {
+  const int longest = std::max(32, round_up32(std::min(c->K, std::max(1, c->max_doc_len))));
+  TRY(shape_for(c, std::min(longest, c->small_row), 4, &c->shape_short));
+  TRY(shape_for(c, longest, 1, &c->shape_long));
   return B200LDA_OK;
 }
 
@@ -267,7 +285,7 @@ int build_tables(b200lda_ctx* c) {
 
 SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_write, uint32_t sweep) {
   SweepParams p{};
-  p.num_docs = c->D;
+  p.doc_order = c->d_doc_order;
   p.doc_ptr = c->d_doc_ptr;
   p.tok_word = c->d_tok_word;
   p.z = c->d_z;
@@ -285,26 +303,42 @@ SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_w
   p.uniforms = nullptr;
   p.layout = c->layout;
   p.K = c->K;
-  p.slot_cap = c->slot_cap;
   p.beta_f = (float)c->beta;
   p.seed = c->cfg.seed;
   p.sweep = sweep;
   p.global_tok_off = c->cfg.global_token_offset;
-  p.doc_counter = c->d_counters + 0;
   p.stats = c->d_counters + 1;
   p.stats_cum = c->d_counters + 5;
   return p;
 }
 
-template <int MODE>
-int launch_sweep(b200lda_ctx* c, const SweepParams& p) {
-  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
-  if (c->tables_in_smem)
-    k_gibbs_sweep<MODE, true><<<c->ctas, c->warps_per_cta * 32, c->smem, c->stream>>>(p);
+template <int MODE, bool LIVE>
+int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
+                 unsigned long long* counter) {
+  if (end <= begin) return B200LDA_OK;
+  p.order_begin = begin;
+  p.order_end = end;
+  p.slot_cap = sh.slot_cap;
+  p.doc_chunk = sh.doc_chunk;
+  p.doc_counter = counter;
+  const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
+  if (sh.tables_in_smem)
+    k_gibbs_sweep<MODE, LIVE, true><<<ctas, sh.warps_per_cta * 32, sh.smem, c->stream>>>(p);
   else
-    k_gibbs_sweep<MODE, false><<<c->ctas, c->warps_per_cta * 32, c->smem, c->stream>>>(p);
+    k_gibbs_sweep<MODE, LIVE, false><<<ctas, sh.warps_per_cta * 32, sh.smem, c->stream>>>(p);
   c->launches += 1;
   CU(cudaGetLastError());
+  return B200LDA_OK;
+}
+
+// One sweep = the long-document class first (few, long-running warps), then the bulk.
+template <int MODE, bool LIVE>
+int launch_sweep(b200lda_ctx* c, const SweepParams& p) {
+  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+  CU(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->stream));
+  TRY((launch_class<MODE, LIVE>(c, p, c->shape_long, 0, c->n_long, c->d_counters + 0)));
+  TRY((launch_class<MODE, LIVE>(c, p, c->shape_short, c->n_long, c->D, c->d_counters + 8)));
   return B200LDA_OK;
 }
 
@@ -424,7 +458,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kStatCounters)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kStatCounters + 1)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
@@ -432,7 +466,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   if (multi)
     if ((rc = dev_alloc_t(c, &c->d_exchange, VK + c->K))) return bail(rc);
   if (cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
-      cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kStatCounters, c->stream) != cudaSuccess)
+      cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * (kStatCounters + 1), c->stream) != cudaSuccess)
     return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
   if ((rc = push_alpha(c))) return bail(rc);
   *out = c;
@@ -451,6 +485,7 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_row_ptr);
   dev_free(c->d_row_nnz);
   dev_free(c->d_rows);
+  dev_free(c->d_doc_order);
   dev_free(c->d_nwk);
   dev_free(c->d_nwk_b);
   dev_free(c->d_nk);
@@ -496,12 +531,32 @@ int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr
     max_len = std::max<int>(max_len, (int)len);
   }
   c->h_row_ptr[num_docs] = off;
+  // visiting order: long-row class first, each class longest document first (counting sort)
+  {
+    const int small = std::min(std::max(32, round_up32(std::min(c->K, std::max(1, max_len)))), c->small_row);
+    std::vector<int64_t> bucket((size_t)max_len + 2, 0);
+    int64_t n_long = 0;
+    for (int64_t d = 0; d < num_docs; ++d) {
+      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+      bucket[(size_t)(max_len - len) + 1]++;  // descending length
+      if (std::min<int64_t>(len, c->K) > small) ++n_long;
+    }
+    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+    c->h_doc_order.resize((size_t)num_docs);
+    for (int64_t d = 0; d < num_docs; ++d) {
+      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+      c->h_doc_order[(size_t)bucket[(size_t)(max_len - len)]++] = (int32_t)d;
+    }
+    c->n_long = n_long;  // longest-first order puts exactly the long class in front
+  }
   c->corpus_loaded = false;
   c->assigned = false;
   if (num_docs > c->cap_docs) {
     dev_free(c->d_doc_ptr);
     dev_free(c->d_row_ptr);
     dev_free(c->d_row_nnz);
+    dev_free(c->d_doc_order);
+    TRY(dev_alloc_t(c, &c->d_doc_order, (size_t)num_docs));
     TRY(dev_alloc_t(c, &c->d_doc_ptr, (size_t)num_docs + 1));
     TRY(dev_alloc_t(c, &c->d_row_ptr, (size_t)num_docs + 1));
     TRY(dev_alloc_t(c, &c->d_row_nnz, (size_t)num_docs));
@@ -527,6 +582,8 @@ int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr
   c->max_doc_len = max_len;
   CU(cudaMemcpyAsync(c->d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_row_ptr, c->h_row_ptr.data(), sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
+  if (num_docs > 0)
+    CU(cudaMemcpyAsync(c->d_doc_order, c->h_doc_order.data(), sizeof(int32_t) * num_docs, cudaMemcpyHostToDevice, c->stream));
   if (N > 0) CU(cudaMemcpyAsync(c->d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
   // word -> token CSR by counting sort; the histogram pass also validates word ids
   TRY(ensure_stage(c, sizeof(unsigned long long) * (size_t)c->V));
@@ -626,7 +683,10 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   // DEFERRED: read the frozen d_nwk, write moves into the copy d_nwk_b.
   // LIVE:     read and write d_nwk in place (d_nwk_b keeps the sweep-start snapshot if multi).
   SweepParams p = sweep_params(c, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
-  TRY(launch_sweep<MODE_UPDATE>(c, p));
+  if (deferred)
+    TRY((launch_sweep<MODE_UPDATE, false>(c, p)));
+  else
+    TRY((launch_sweep<MODE_UPDATE, true>(c, p)));
   CU(cudaEventRecord(c->ev[2], c->stream));
   if (multi) {
     const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;
@@ -713,7 +773,7 @@ int b200lda_sample_frozen(b200lda_ctx* c, const float* uniforms, uint32_t sweep,
   p.nwk_write = nullptr;
   p.z_out = d_zout;
   p.uniforms = uniforms ? d_u : nullptr;
-  TRY(launch_sweep<MODE_FROZEN>(c, p));
+  TRY((launch_sweep<MODE_FROZEN, false>(c, p)));
   CU(cudaMemcpyAsync(z_out, d_zout, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
@@ -896,10 +956,13 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->kernel_launches = c->launches;
   out->tokens_sampled = c->tokens_sampled;
   out->device_bytes = c->device_bytes;
-  out->smem_bytes_per_cta = (int32_t)c->smem;
-  out->warps_per_cta = c->warps_per_cta;
-  out->ctas = c->ctas;
-  out->slot_capacity = c->slot_cap;
+  out->smem_bytes_per_cta = (int32_t)c->shape_short.smem;
+  out->warps_per_cta = c->shape_short.warps_per_cta;
+  out->ctas = c->shape_short.ctas;
+  out->slot_capacity = c->shape_short.slot_cap;
+  out->long_docs = c->n_long;
+  out->long_slot_capacity = c->shape_long.slot_cap;
+  out->long_ctas = c->shape_long.ctas;
   if (c->in_sweep) return B200LDA_OK;  // timings of an open sweep are not resolvable yet
   TRY(resolve_events(c));
   out->last_tables_ms = c->last_tables_ms;

@@ -12,8 +12,12 @@
 //     resolved by a fan-out-32 search = one coalesced 128-byte line per level;
 //   * randomness: Philox keyed by (seed; global token, sweep), 32 tokens per warp batch, one
 //     lane each, so the RNG costs ~2 instructions per token;
-//   * count moves: 16-bit row edit in shared memory, integer RED atomics on n_wk / n_k deltas.
-// MODE_UPDATE serves both LIVE (nwk_read == nwk_write) and DEFERRED (distinct buffers);
+//   * count moves: one pass over the part of the 16-bit row between the slot that empties and
+//     the slot that appears, integer RED atomics on n_wk / n_k deltas.
+// Documents are visited through doc_order (longest first); the host launches the kernel once per
+// document class so that short documents get small per-warp rows and therefore high occupancy.
+// MODE_UPDATE serves LIVE (LIVE=true: n_wk read through L2 and written in place) and DEFERRED
+// (LIVE=false: frozen n_wk through the read-only path, moves go to a second buffer);
 // MODE_FROZEN moves nothing (north-star parity mode).
 #pragma once
 #include "device_common.cuh"
@@ -23,7 +27,8 @@ namespace b200lda {
 enum { MODE_UPDATE = 0, MODE_FROZEN = 1 };
 
 struct SweepParams {
-  int64_t num_docs;
+  const int32_t* doc_order;   // [D] document ids, class by class, longest first
+  int64_t order_begin, order_end;  // this launch's slice of doc_order
   const int64_t* doc_ptr;     // [D+1] token offsets (document order)
   const int32_t* tok_word;    // [N]
   uint16_t* z;                // [N] current topics (updated in MODE_UPDATE)
@@ -32,7 +37,7 @@ struct SweepParams {
   int32_t* row_nnz;           // [D]
   uint32_t* rows;             // packed (topic << 16 | count), ascending topic
   const int32_t* nwk_read;    // [V*K]
-  int32_t* nwk_write;         // [V*K] (== nwk_read in LIVE mode)
+  int32_t* nwk_write;         // [V*K] (== nwk_read when LIVE)
   int32_t* nk_delta;          // [K]
   const float* invden;        // [K]  1 / (n_k + V beta)
   const float* ab;            // [K]  alpha_k * invden_k
@@ -42,18 +47,40 @@ struct SweepParams {
   PriorLayout layout;
   int K;
   int slot_cap;               // shared-memory slots per warp (multiple of 32)
+  int doc_chunk;              // documents fetched per scheduler atomic
   float beta_f;
   uint64_t seed;
   uint32_t sweep;
   int64_t global_tok_off;
-  unsigned long long* doc_counter;  // dynamic document scheduler
+  unsigned long long* doc_counter;  // dynamic document scheduler (starts at 0 for each launch)
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
 };
 
-constexpr int kDocChunk = 4;
+// Rows [a, b) move one slot up (to [a+1, b+1)); chunks from the top so nothing is overwritten.
+__device__ __forceinline__ void row_shift_up(uint32_t* slots, int a, int b, int lane) {
+  for (int hi = b - 1; hi >= a; hi -= 32) {
+    const int j = hi - lane;
+    uint32_t v = 0u;
+    if (j >= a) v = slots[j];
+    __syncwarp();
+    if (j >= a) slots[j + 1] = v;
+    __syncwarp();
+  }
+}
+// Rows [a, b) move one slot down (to [a-1, b-1)); chunks from the bottom.
+__device__ __forceinline__ void row_shift_down(uint32_t* slots, int a, int b, int lane) {
+  for (int lo = a; lo < b; lo += 32) {
+    const int j = lo + lane;
+    uint32_t v = 0u;
+    if (j < b) v = slots[j];
+    __syncwarp();
+    if (j < b) slots[j - 1] = v;
+    __syncwarp();
+  }
+}
 
-template <int MODE, bool TABLES_IN_SMEM>
+template <int MODE, bool LIVE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -66,33 +93,31 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
   uint32_t* slots = reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)warp * p.slot_cap;
   float* pref = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(s_tab + tab_floats) +
                                          (size_t)nwarps * p.slot_cap) + (size_t)warp * p.slot_cap;
-  const float* t_invden;
-  const float* t_ab;
   if (TABLES_IN_SMEM) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       s_tab[k] = p.invden[k];
       s_tab[K + k] = p.ab[k];
     }
     __syncthreads();
-    t_invden = s_tab;
-    t_ab = s_tab + K;
-  } else {
-    t_invden = p.invden;
-    t_ab = p.ab;
   }
+  // fp32 masks that make the Kogge-Stone step "if (lane >= d) v += y" one FFMA: v = y*m + v is
+  // exactly v + y (m = 1, one rounding) or exactly v (m = 0).
+  const float m1 = lane >= 1 ? 1.0f : 0.0f, m2 = lane >= 2 ? 1.0f : 0.0f, m4 = lane >= 4 ? 1.0f : 0.0f,
+              m8 = lane >= 8 ? 1.0f : 0.0f, m16 = lane >= 16 ? 1.0f : 0.0f;
 
-  const bool live = (p.nwk_read == p.nwk_write);
   const float beta_f = p.beta_f;
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
+  const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
 
   for (;;) {
-    unsigned long long d0 = 0;
-    if (lane == 0) d0 = atomicAdd(p.doc_counter, (unsigned long long)kDocChunk);
-    d0 = __shfl_sync(kFullMask, d0, 0);
-    if ((int64_t)d0 >= p.num_docs) break;
-    const int64_t d1 = min((int64_t)d0 + kDocChunk, p.num_docs);
+    unsigned long long c0 = 0;
+    if (lane == 0) c0 = atomicAdd(p.doc_counter, (unsigned long long)p.doc_chunk);
+    c0 = __shfl_sync(kFullMask, c0, 0);
+    if (c0 >= ndocs) break;
+    const unsigned long long c1 = min(c0 + (unsigned long long)p.doc_chunk, ndocs);
 
-    for (int64_t d = (int64_t)d0; d < d1; ++d) {
+    for (unsigned long long ci = c0; ci < c1; ++ci) {
+      const int64_t d = (int64_t)__ldg(p.doc_order + p.order_begin + (int64_t)ci);
       const int64_t tb = p.doc_ptr[d], te = p.doc_ptr[d + 1];
       if (te == tb) continue;
       const int64_t rp = p.row_ptr[d];
@@ -128,42 +153,46 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
           // ---- doc bucket: weights + tile scan --------------------------------------------
           const int ntiles = (nnz + 31) >> 5;
           float carry = 0.0f, P = 0.0f;
-          int jo = -1;
+          int jo = 0;
           for (int tile = 0; tile < ntiles; ++tile) {
             const int j = (tile << 5) + lane;
             const bool act = j < nnz;
-            const uint32_t s = act ? slots[j] : 0u;
-            const int topic = (int)(s >> 16);
+            const uint32_t s = slots[j];  // j < slot_cap always; slots past nnz hold stale rows
+            const int topic = act ? (int)(s >> 16) : 0;
             int c = (int)(s & 0xffffu);
             int n = 0;
-            if (act) n = live ? __ldcg(nrow + topic) : __ldg(nrow + topic);
+            if (act) n = LIVE ? __ldcg(nrow + topic) : __ldg(nrow + topic);
             const bool is_old = act && (topic == o);
             const unsigned bo = __ballot_sync(kFullMask, is_old);
             if (bo) jo = (tile << 5) + __ffs(bo) - 1;
-            if (is_old) {
-              c -= 1;
-              n = max(n - 1, 0);
-            }
-            float a = 0.0f;
-            if (act) a = fmul(fmul(fadd((float)n, beta_f), t_invden[topic]), (float)c);
-            a = warp_scan_inclusive(a, lane);
+            c -= (int)is_old;
+            n = max(n - (int)is_old, 0);
+            const float inv = TABLES_IN_SMEM ? s_tab[topic] : __ldg(p.invden + topic);
+            float a = fmul(fmul(fadd((float)n, beta_f), inv), (float)c);
+            a = act ? a : 0.0f;
+            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), m1, a);
+            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), m2, a);
+            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), m4, a);
+            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), m8, a);
+            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), m16, a);
             P = fadd(carry, a);
-            if (ntiles > 1 && act) pref[j] = P;
+            if (ntiles > 1) pref[j] = P;
             carry = __shfl_sync(kFullMask, P, 31);
           }
           const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
-          const float delta = t_ab[o];
+          const float delta = TABLES_IN_SMEM ? s_tab[K + o] : __ldg(p.ab + o);
           float qp = fsub(qw, delta);
           qp = qp < 0.0f ? 0.0f : qp;
           const float T = fadd(A, qp);
           const float x = fmul(u, T);
 
           int newt;
+          int jn = -1;  // slot of newt when it is already known to be in the row
           if (x < A) {
-            int jj = nnz - 1;
+            jn = nnz - 1;
             if (ntiles == 1) {
               const unsigned b = __ballot_sync(kFullMask, (lane < nnz) && (P > x));
-              if (b) jj = __ffs(b) - 1;
+              if (b) jn = __ffs(b) - 1;
             } else {
               __syncwarp();
               for (int tile = 0; tile < ntiles; ++tile) {
@@ -171,12 +200,12 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
                 const bool hit = (j < nnz) && (pref[j] > x);
                 const unsigned b = __ballot_sync(kFullMask, hit);
                 if (b) {
-                  jj = (tile << 5) + __ffs(b) - 1;
+                  jn = (tile << 5) + __ffs(b) - 1;
                   break;
                 }
               }
             }
-            newt = (int)(slots[jj] >> 16);
+            newt = (int)(slots[jn] >> 16);
           } else {
             // ---- prior bucket: skip the own-token mass delta at topic o, then search ----------
             ++st_prior;
@@ -199,51 +228,48 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
 
           if (MODE == MODE_UPDATE && newt != o) {
             ++st_moved;
-            // 1) take the token out of topic o (delete the slot if it empties)
+            // Where does newt live (or go) in the row as it stands, old slot still present?
+            int pos = 0;
+            if (jn < 0) {
+              for (int tile = 0; (tile << 5) < nnz; ++tile) {
+                const int j = (tile << 5) + lane;
+                const bool act = j < nnz;
+                const int topic = act ? (int)(slots[j] >> 16) : 0x7fffffff;
+                const unsigned less = __ballot_sync(kFullMask, topic < newt);
+                const unsigned eq = __ballot_sync(kFullMask, topic == newt);
+                pos += __popc(less);
+                if (eq) jn = (tile << 5) + __ffs(eq) - 1;
+                if (eq || less != kFullMask) break;
+              }
+            }
             const uint32_t so = slots[jo];
+            const bool del = (so & 0xffffu) == 1u;
             __syncwarp();
-            if ((so & 0xffffu) == 1u) {
-              for (int lo = jo; lo < nnz - 1; lo += 32) {
-                const int j = lo + lane;
-                uint32_t v = 0u;
-                if (j < nnz - 1) v = slots[j + 1];
-                __syncwarp();
-                if (j < nnz - 1) slots[j] = v;
-                __syncwarp();
+            if (jn >= 0) {                 // newt already has a slot: bump it
+              if (lane == 0) {
+                slots[jn] += 1u;
+                if (!del) slots[jo] = so - 1u;
               }
-              --nnz;
-            } else if (lane == 0) {
-              slots[jo] = so - 1u;
-            }
-            __syncwarp();
-            // 2) put it into topic newt (insert a slot, keeping ascending topic order)
-            int pos = 0, found = -1;
-            for (int tile = 0; (tile << 5) < nnz; ++tile) {
-              const int j = (tile << 5) + lane;
-              const bool act = j < nnz;
-              const int topic = act ? (int)(slots[j] >> 16) : 0x7fffffff;
-              const unsigned less = __ballot_sync(kFullMask, act && topic < newt);
-              const unsigned eq = __ballot_sync(kFullMask, act && topic == newt);
-              pos += __popc(less);
-              if (eq) found = (tile << 5) + __ffs(eq) - 1;
-              if (eq || less != kFullMask) break;
-            }
-            if (found >= 0) {
-              if (lane == 0) slots[found] += 1u;
-            } else {
-              for (int hi = nnz - 1; hi >= pos; hi -= 32) {
-                const int j = hi - lane;
-                uint32_t v = 0u;
-                if (j >= pos) v = slots[j];
+              if (del) {                   // ... and close the gap the old topic leaves
                 __syncwarp();
-                if (j >= pos) slots[j + 1] = v;
-                __syncwarp();
+                row_shift_down(slots, jo + 1, nnz, lane);
+                --nnz;
               }
+            } else if (!del) {             // new slot, old one stays
+              if (lane == 0) slots[jo] = so - 1u;
+              __syncwarp();
+              row_shift_up(slots, pos, nnz, lane);
               if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
               ++nnz;
+            } else if (pos <= jo) {        // old slot empties, new one appears below it
+              row_shift_up(slots, pos, jo, lane);
+              if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
+            } else {                       // ... or above it
+              row_shift_down(slots, jo + 1, pos, lane);
+              if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
             }
             __syncwarp();
-            // 3) word-topic and topic totals: integer RED atomics (order-independent sums)
+            // word-topic and topic totals: integer RED atomics (order-independent sums)
             if (lane == 0) {
               int32_t* wrow = p.nwk_write + (size_t)w * K;
               atomicAdd(wrow + o, -1);
