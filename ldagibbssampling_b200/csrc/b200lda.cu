@@ -437,6 +437,13 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->beta = cfg->beta;
   c->sm_count = prop.multiProcessorCount;
   c->layout = make_layout(c->K);
+  {
+    // Short-row class: the widest row that still lets 4 CTAs of 8 warps share an SM's shared
+    // memory (the kernel's registers allow no more than 4 anyway), so it never costs occupancy.
+    const int64_t tab = 2 * (int64_t)sizeof(float) * c->K;
+    const int64_t cap4 = (((int64_t)kMaxSmemPerCta / 4 - 1024 - tab) / 64) & ~(int64_t)31;
+    c->small_row = (int)std::max<int64_t>(256, std::min<int64_t>(cap4, 65536));
+  }
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {

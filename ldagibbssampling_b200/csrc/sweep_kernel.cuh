@@ -57,6 +57,8 @@ struct SweepParams {
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
 };
 
+constexpr int kGroup = 4;  // tiles whose gathers are in flight together
+
 // Rows [a, b) move one slot up (to [a+1, b+1)); chunks from the top so nothing is overwritten.
 __device__ __forceinline__ void row_shift_up(uint32_t* slots, int a, int b, int lane) {
   for (int hi = b - 1; hi >= a; hi -= 32) {
@@ -151,33 +153,48 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
           st_nnz += (unsigned)nnz;
 
           // ---- doc bucket: weights + tile scan --------------------------------------------
+          // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any
+          // is consumed, so a multi-tile row pays one memory latency per group, not per tile.
           const int ntiles = (nnz + 31) >> 5;
           float carry = 0.0f, P = 0.0f;
           int jo = 0;
-          for (int tile = 0; tile < ntiles; ++tile) {
-            const int j = (tile << 5) + lane;
-            const bool act = j < nnz;
-            const uint32_t s = slots[j];  // j < slot_cap always; slots past nnz hold stale rows
-            const int topic = act ? (int)(s >> 16) : 0;
-            int c = (int)(s & 0xffffu);
-            int n = 0;
-            if (act) n = LIVE ? __ldcg(nrow + topic) : __ldg(nrow + topic);
-            const bool is_old = act && (topic == o);
-            const unsigned bo = __ballot_sync(kFullMask, is_old);
-            if (bo) jo = (tile << 5) + __ffs(bo) - 1;
-            c -= (int)is_old;
-            n = max(n - (int)is_old, 0);
-            const float inv = TABLES_IN_SMEM ? s_tab[topic] : __ldg(p.invden + topic);
-            float a = fmul(fmul(fadd((float)n, beta_f), inv), (float)c);
-            a = act ? a : 0.0f;
-            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), m1, a);
-            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), m2, a);
-            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), m4, a);
-            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), m8, a);
-            a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), m16, a);
-            P = fadd(carry, a);
-            if (ntiles > 1) pref[j] = P;
-            carry = __shfl_sync(kFullMask, P, 31);
+          for (int t0 = 0; t0 < ntiles; t0 += kGroup) {
+            uint32_t sv[kGroup];
+            int nv[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+              const int j = ((t0 + g) << 5) + lane;
+              sv[g] = 0u;
+              nv[g] = 0;
+              if (j < nnz) {
+                sv[g] = slots[j];
+                const int32_t* cell = nrow + (sv[g] >> 16);
+                nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+              if (t0 + g < ntiles) {
+                const int j = ((t0 + g) << 5) + lane;
+                const bool act = j < nnz;
+                const int topic = (int)(sv[g] >> 16);
+                const bool is_old = act && (topic == o);
+                const unsigned bo = __ballot_sync(kFullMask, is_old);
+                if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
+                const int c = (int)(sv[g] & 0xffffu) - (int)is_old;
+                const int n = max(nv[g] - (int)is_old, 0);
+                const float inv = TABLES_IN_SMEM ? s_tab[topic] : __ldg(p.invden + topic);
+                float a = fmul(fmul(fadd((float)n, beta_f), inv), (float)c);  // c == 0 past nnz
+                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), m1, a);
+                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), m2, a);
+                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), m4, a);
+                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), m8, a);
+                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), m16, a);
+                P = fadd(carry, a);
+                if (ntiles > 1) pref[j] = P;
+                carry = __shfl_sync(kFullMask, P, 31);
+              }
+            }
           }
           const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
           const float delta = TABLES_IN_SMEM ? s_tab[K + o] : __ldg(p.ab + o);
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
             ++st_prior;
             const float y = fsub(x, A);
             const float* prow = p.prior + (size_t)w * p.layout.stride;
-            const float po = __ldg(prow + p.layout.off[0] + o);
+            const float po = __ldg(prow + o);  // level 0 sits at offset 0
             const float pod = fsub(po, delta);
             const float s = (y < pod) ? y : fadd(y, delta);
             int block = 0;
