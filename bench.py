@@ -244,6 +244,15 @@ def b200_arm(args):
         ptr, n = s.exchange_buffer()
         ex = torch.as_tensor(_DevBuf(ptr, n), device=dev)
 
+    def sync_counts():
+        # every shard counted only its own documents: sum once so all n_wk / n_k replicas are global
+        if ex is not None:
+            s.counts_sync_begin()
+            dist.all_reduce(ex, op=dist.ReduceOp.SUM)
+            s.counts_sync_end()
+
+    sync_counts()
+
     def one_sweep():
         s.sweep_begin()
         if ex is not None:
@@ -332,6 +341,7 @@ def b200_arm(args):
         t0 = time.perf_counter()
         s.load_corpus_raw(shard.num_docs, h_doc_ptr.data_ptr(), h_words.data_ptr(), shard.num_tokens)
         s.init_assignments_raw(h_z.data_ptr())
+        sync_counts()
         one_sweep()
         s.assignments_raw(h_z.data_ptr())
         fence()

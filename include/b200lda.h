@@ -139,6 +139,13 @@ int b200lda_sweep(b200lda_ctx* ctx, int32_t n);
 int b200lda_sweep_begin(b200lda_ctx* ctx);
 int b200lda_exchange_buffer(b200lda_ctx* ctx, void** d_buf, int64_t* count);
 int b200lda_sweep_end(b200lda_ctx* ctx);
+/* Once after b200lda_init_assignments on every shard of a multi-shard model (Mallet's
+ * sumTypeTopicCounts at start-up): each shard built n_wk / n_k from its own documents only;
+ *   counts_sync_begin  copies them into the exchange buffer,
+ *   the caller sums the exchange buffer over all shards (same all-reduce as per sweep),
+ *   counts_sync_end    installs the sum as the n_wk / n_k replica. */
+int b200lda_counts_sync_begin(b200lda_ctx* ctx);
+int b200lda_counts_sync_end(b200lda_ctx* ctx);
 int b200lda_synchronize(b200lda_ctx* ctx);
 int b200lda_get_stream(b200lda_ctx* ctx, void** stream);
 
@@ -146,6 +153,16 @@ int b200lda_get_stream(b200lda_ctx* ctx, void** stream);
  * against the current counts WITHOUT moving any count. uniforms == NULL uses Philox with the
  * given sweep number; otherwise uniforms[i] in [0,1) is token i's draw. */
 int b200lda_sample_frozen(b200lda_ctx* ctx, const float* uniforms, uint32_t sweep, int32_t* z_out);
+
+/* model.getInferencer().getSampledDistribution(instance, iterations, thinning, burnIn)
+ *                                                          cmu_ron/TrainAndPredict.java:144,
+ * batched: num_docs held-out documents in one device pass against the frozen   cmu/…:114
+ * n_wk / n_k / alpha / beta of this context (word ids must be < V: drop unknown types first, as
+ * Mallet does). theta: num_docs * K doubles, row d = normalised average of (alpha_k + n_dk) over
+ * the samples kept at iterations it > burn_in with (it - burn_in) % thinning == 0 (the final
+ * state if none). Does not touch the training chain. */
+int b200lda_infer(b200lda_ctx* ctx, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word,
+                  int32_t iterations, int32_t thinning, int32_t burn_in, uint64_t seed, double* theta);
 
 /* model.modelLogLikelihood()                               cmu_ron/TrainAndPredict.java:234,
  * world_size > 1: *out is this shard's document part plus the (replicated)    cmu/…:436

@@ -72,6 +72,9 @@ SYMBOLS = [
     ("b200lda_sweep_begin", C.c_int, [_P]),
     ("b200lda_exchange_buffer", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     ("b200lda_sweep_end", C.c_int, [_P]),
+    ("b200lda_counts_sync_begin", C.c_int, [_P]),
+    ("b200lda_counts_sync_end", C.c_int, [_P]),
+    ("b200lda_infer", C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P]),
     ("b200lda_synchronize", C.c_int, [_P]),
     ("b200lda_get_stream", C.c_int, [_P, C.POINTER(_P)]),
     ("b200lda_sample_frozen", C.c_int, [_P, _P, C.c_uint32, _P]),
@@ -130,6 +133,7 @@ class Sampler:
                      world_size=world_size, reserved0=0, global_token_offset=global_token_offset,
                      global_doc_offset=global_doc_offset, stream=stream)
         self.K, self.V = num_topics, num_types
+        self.device = device
         self.num_docs = 0
         self.num_tokens = 0
         self._check(self._lib.b200lda_create(C.byref(cfg), C.byref(self._h)))
@@ -185,6 +189,22 @@ class Sampler:
 
     def sweep_end(self):
         self._check(self._lib.b200lda_sweep_end(self._h))
+
+    def counts_sync_begin(self):
+        self._check(self._lib.b200lda_counts_sync_begin(self._h))
+
+    def counts_sync_end(self):
+        self._check(self._lib.b200lda_counts_sync_end(self._h))
+
+    def infer(self, doc_ptr, tok_word, iterations=100, thinning=10, burn_in=10, seed=0):
+        """TopicInferencer.getSampledDistribution for a batch of held-out documents: D x K thetas."""
+        doc_ptr = np.ascontiguousarray(doc_ptr, np.int64)
+        tok_word = np.ascontiguousarray(tok_word, np.int32)
+        nd = len(doc_ptr) - 1
+        theta = np.empty((nd, self.K), np.float64)
+        self._check(self._lib.b200lda_infer(self._h, nd, _ptr(doc_ptr), _ptr(tok_word), iterations, thinning,
+                                            burn_in, seed, _ptr(theta)))
+        return theta
 
     def synchronize(self):
         self._check(self._lib.b200lda_synchronize(self._h))

@@ -47,16 +47,18 @@ int fail(int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-#define TRY(expr)            \
-  do {                       \
-    int rc__ = (expr);       \
+#define TRY(expr)                        \
+  do {                                   \
+    int rc__ = (expr);                   \
     if (rc__ != B200LDA_OK) return rc__; \
   } while (0)
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
-// [0] doc scheduler, [1..3] last sweep {moved, prior draws, nnz sum}, [4] nnz(n_wk), [5..7] cumulative {same three}
-constexpr int kStatCounters = 8;   // (+1: [8] second scheduler counter)
+// d_counters: [0] scheduler (long class), [1..3] last sweep {moved, prior draws, nnz sum},
+// [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
+constexpr int kCounters = 12;  // [9..11] sink for the stats of inference passes
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
+constexpr int kPartial = 1184;   // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
 
 int round_up32(int x) { return (x + 31) & ~31; }
 
@@ -79,8 +81,6 @@ PriorLayout make_layout(int K) {
   return L;
 }
 
-}  // namespace
-
 // Launch shape of the sampling kernel for one document class.
 struct SweepShape {
   int slot_cap = 32, warps_per_cta = 8, ctas = 0, doc_chunk = 4;
@@ -88,29 +88,40 @@ struct SweepShape {
   bool tables_in_smem = true;
 };
 
+// A packed, device-resident set of documents: the training corpus of a context, or a batch of
+// held-out documents during inference.
+struct DeviceCorpus {
+  int64_t D = 0, N = 0;
+  int64_t* d_doc_ptr = nullptr;   // [D+1]
+  int32_t* d_tok_word = nullptr;  // [N]   doc -> token order
+  uint16_t* d_z = nullptr;        // [N]
+  int64_t* d_row_ptr = nullptr;   // [D+1] packed n_dk row offsets (capacity min(K, L_d))
+  int32_t* d_row_nnz = nullptr;   // [D]
+  uint32_t* d_rows = nullptr;     // [cap_rows]
+  int32_t* d_doc_order = nullptr; // [D]   long-row class first, longest first
+  long long* d_word_ptr = nullptr;  // [V+1] word -> token CSR (training corpus only)
+  int64_t* d_wtok = nullptr;        // [N]
+  int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
+  int64_t n_long = 0;
+  int max_doc_len = 0;
+  std::vector<int64_t> h_doc_ptr, h_row_ptr;
+  std::vector<int32_t> h_doc_order;
+  SweepShape shape_short, shape_long;
+};
+
+}  // namespace
+
 struct b200lda_ctx {
   b200lda_config cfg{};
   int K = 0, V = 0;
-  int64_t D = 0, N = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
   int64_t device_bytes = 0;
   int64_t launches = 0;
 
-  // corpus
-  int64_t* d_doc_ptr = nullptr;
-  int32_t* d_tok_word = nullptr;
-  uint16_t* d_z = nullptr;
-  long long* d_word_ptr = nullptr;
-  int64_t* d_wtok = nullptr;
-  int64_t* d_row_ptr = nullptr;
-  int32_t* d_row_nnz = nullptr;
-  uint32_t* d_rows = nullptr;
-  int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
-  std::vector<int64_t> h_doc_ptr, h_row_ptr;
-  std::vector<int32_t> h_doc_order;
-  int max_doc_len = 0;
+  DeviceCorpus corp;  // training documents
+  int small_row = 256;
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
@@ -129,29 +140,20 @@ struct b200lda_ctx {
   uint32_t* d_hist_scratch = nullptr;
   size_t hist_scratch_bytes = 0;
 
-  // sweep launch shapes, one per document class; doc_order lists the long class first
-  SweepShape shape_short, shape_long;
-  int32_t* d_doc_order = nullptr;
-  int64_t n_long = 0;
-  int small_row = 256;
-
   // state
-  bool corpus_loaded = false, assigned = false, in_sweep = false;
+  bool corpus_loaded = false, assigned = false, in_sweep = false, in_sync = false;
   int64_t sweeps_done = 0, tokens_sampled = 0;
-  unsigned long long last_moved = 0, last_prior = 0, last_nnz_sum = 0;
   // per-sweep device timing: 4 events per sweep (begin, tables done, sample done, end), resolved
   // lazily at b200lda_get_stats so no sweep ever synchronises for bookkeeping
   std::vector<cudaEvent_t> ev_pool;
   int ev_pending = 0;
-  cudaEvent_t* ev = nullptr;  // the current sweep's quadruple
+  cudaEvent_t* ev = nullptr;
   double cum_tables_ms = 0, cum_sample_ms = 0, cum_finish_ms = 0;
   double last_tables_ms = 0, last_sample_ms = 0, last_finish_ms = 0;
   int64_t cum_sweeps = 0;
 };
 
 namespace {
-
-constexpr int kPartial = 1184;  // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
 
 int dev_alloc(b200lda_ctx* c, void** p, size_t bytes) {
   *p = nullptr;
@@ -215,6 +217,8 @@ int push_alpha(b200lda_ctx* c) {
   return B200LDA_OK;
 }
 
+// ---- sampling-kernel launch shapes ----------------------------------------------------------
+
 template <int MODE, bool LIVE, bool TS>
 int sweep_occupancy(int threads, size_t smem, int* occ) {
   CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, LIVE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -225,7 +229,7 @@ int sweep_occupancy(int threads, size_t smem, int* occ) {
 
 // Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
 // of slot_cap entries each.
-int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, SweepShape* out) {
+int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepShape* out) {
   SweepShape sh;
   sh.slot_cap = slot_cap;
   sh.doc_chunk = doc_chunk;
@@ -245,7 +249,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, SweepShape* out) {
   }
   if (!ok)
     return fail(B200LDA_ERANGE, "document rows of %d slots do not fit shared memory (K=%d, longest doc=%d)",
-                slot_cap, c->K, c->max_doc_len);
+                slot_cap, c->K, longest);
   const int threads = sh.warps_per_cta * 32;
   int occ[3] = {0, 0, 0};
   if (sh.tables_in_smem) {
@@ -263,14 +267,158 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, SweepShape* out) {
   return B200LDA_OK;
 }
 
-// Two document classes: rows of at most kSmallRow slots (the bulk: small per-warp shared memory,
-// high occupancy) and the long tail (rows up to min(K, longest document)).
-int configure_sweep(b200lda_ctx* c) {
-  const int longest = std::max(32, round_up32(std::min(c->K, std::max(1, c->max_doc_len))));
-  TRY(shape_for(c, std::min(longest, c->small_row), 4, &c->shape_short));
-  TRY(shape_for(c, longest, 1, &c->shape_long));
+// Two document classes: rows of at most small_row slots (the bulk: small per-warp shared memory,
+// full occupancy) and the long tail (rows up to min(K, longest document)).
+int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp) {
+  const int longest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
+  TRY(shape_for(c, std::min(longest, c->small_row), 4, cp.max_doc_len, &cp.shape_short));
+  TRY(shape_for(c, longest, 1, cp.max_doc_len, &cp.shape_long));
   return B200LDA_OK;
 }
+
+// ---- corpus packing ---------------------------------------------------------------------------
+
+void free_corpus(DeviceCorpus& cp) {
+  dev_free(cp.d_doc_ptr);
+  dev_free(cp.d_tok_word);
+  dev_free(cp.d_z);
+  dev_free(cp.d_row_ptr);
+  dev_free(cp.d_row_nnz);
+  dev_free(cp.d_rows);
+  dev_free(cp.d_doc_order);
+  dev_free(cp.d_word_ptr);
+  dev_free(cp.d_wtok);
+  cp.cap_docs = cp.cap_tokens = cp.cap_rows = 0;
+}
+
+// Validates the CSR, plans the packed n_dk rows (capacity min(K, L_d)) and the visiting order
+// (long-row class first, each class longest document first — a counting sort), uploads
+// everything. `with_word_order` adds the word -> token CSR (device counting sort; its histogram
+// pass also validates the word ids).
+int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word,
+                bool with_word_order) {
+  if (num_docs < 0 || !doc_ptr) return fail(B200LDA_EINVAL, "bad corpus arguments");
+  if (doc_ptr[0] != 0) return fail(B200LDA_EINVAL, "doc_ptr[0] must be 0");
+  const int64_t N = doc_ptr[num_docs];
+  if (N > 0 && !tok_word) return fail(B200LDA_EINVAL, "tok_word is null");
+  cp.h_doc_ptr.assign(doc_ptr, doc_ptr + num_docs + 1);
+  cp.h_row_ptr.resize(num_docs + 1);
+  int max_len = 0;
+  int64_t off = 0;
+  for (int64_t d = 0; d < num_docs; ++d) {
+    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", (long long)d);
+    if (len > 65535) return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", (long long)d, (long long)len);
+    cp.h_row_ptr[d] = off;
+    off += std::min<int64_t>(len, c->K);
+    max_len = std::max<int>(max_len, (int)len);
+  }
+  cp.h_row_ptr[num_docs] = off;
+  {
+    const int small = std::min(std::max(32, round_up32(std::min(c->K, std::max(1, max_len)))), c->small_row);
+    std::vector<int64_t> bucket((size_t)max_len + 2, 0);
+    int64_t n_long = 0;
+    for (int64_t d = 0; d < num_docs; ++d) {
+      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+      bucket[(size_t)(max_len - len) + 1]++;  // descending length
+      if (std::min<int64_t>(len, c->K) > small) ++n_long;
+    }
+    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+    cp.h_doc_order.resize((size_t)num_docs);
+    for (int64_t d = 0; d < num_docs; ++d) {
+      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+      cp.h_doc_order[(size_t)bucket[(size_t)(max_len - len)]++] = (int32_t)d;
+    }
+    cp.n_long = n_long;  // longest-first order puts exactly the long class in front
+  }
+  if (num_docs > cp.cap_docs) {
+    dev_free(cp.d_doc_ptr);
+    dev_free(cp.d_row_ptr);
+    dev_free(cp.d_row_nnz);
+    dev_free(cp.d_doc_order);
+    TRY(dev_alloc_t(c, &cp.d_doc_order, (size_t)num_docs));
+    TRY(dev_alloc_t(c, &cp.d_doc_ptr, (size_t)num_docs + 1));
+    TRY(dev_alloc_t(c, &cp.d_row_ptr, (size_t)num_docs + 1));
+    TRY(dev_alloc_t(c, &cp.d_row_nnz, (size_t)num_docs));
+    cp.cap_docs = num_docs;
+  }
+  if (N > cp.cap_tokens) {
+    dev_free(cp.d_tok_word);
+    dev_free(cp.d_z);
+    dev_free(cp.d_wtok);
+    TRY(dev_alloc_t(c, &cp.d_tok_word, (size_t)N));
+    TRY(dev_alloc_t(c, &cp.d_z, (size_t)N));
+    if (with_word_order) TRY(dev_alloc_t(c, &cp.d_wtok, (size_t)N));
+    cp.cap_tokens = N;
+  }
+  if (off > cp.cap_rows) {
+    dev_free(cp.d_rows);
+    TRY(dev_alloc_t(c, &cp.d_rows, (size_t)off));
+    cp.cap_rows = off;
+  }
+  cp.D = num_docs;
+  cp.N = N;
+  cp.max_doc_len = max_len;
+  CU(cudaMemcpyAsync(cp.d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(cp.d_row_ptr, cp.h_row_ptr.data(), sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
+  if (num_docs > 0)
+    CU(cudaMemcpyAsync(cp.d_doc_order, cp.h_doc_order.data(), sizeof(int32_t) * num_docs, cudaMemcpyHostToDevice, c->stream));
+  if (N > 0) CU(cudaMemcpyAsync(cp.d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+
+  TRY(ensure_stage(c, sizeof(unsigned long long) * (size_t)c->V));
+  unsigned long long* d_wcount = reinterpret_cast<unsigned long long*>(c->d_stage);
+  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  if (N > 0) {
+    k_word_hist<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, cp.d_tok_word, d_wcount, c->d_bad);
+    c->launches += 1;
+  }
+  if (with_word_order) {
+    if (!cp.d_word_ptr) TRY(dev_alloc_t(c, &cp.d_word_ptr, (size_t)c->V + 1));
+    k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>(c->V, d_wcount, cp.d_word_ptr);
+    c->launches += 1;
+  }
+  int bad = 0;
+  CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (bad) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
+  if (with_word_order && N > 0) {
+    CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
+    k_word_scatter<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, cp.d_tok_word, cp.d_word_ptr, d_wcount, cp.d_wtok);
+    c->launches += 1;
+  }
+  CU(cudaGetLastError());
+  TRY(configure_sweep(c, cp));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+// Packed ascending-topic n_dk rows from cp.d_z.
+int build_doc_rows(b200lda_ctx* c, DeviceCorpus& cp) {
+  if (cp.D == 0) return B200LDA_OK;
+  const int wpc = 8;
+  const size_t hist_smem = sizeof(uint32_t) * (size_t)c->K * wpc;
+  const int grid = grid_for(c, cp.D * 32, 256, hist_smem <= 48 * 1024 ? 8 : 2);
+  if (hist_smem <= 96 * 1024) {
+    CU(cudaFuncSetAttribute(k_build_doc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    k_build_doc_rows<<<grid, wpc * 32, hist_smem, c->stream>>>(cp.D, c->K, cp.d_doc_ptr, cp.d_z, cp.d_row_ptr,
+                                                             cp.d_row_nnz, cp.d_rows, nullptr);
+  } else {
+    const size_t need = sizeof(uint32_t) * (size_t)c->K * wpc * grid;
+    if (need > c->hist_scratch_bytes) {
+      dev_free(c->d_hist_scratch);
+      TRY(dev_alloc(c, reinterpret_cast<void**>(&c->d_hist_scratch), need));
+      c->hist_scratch_bytes = need;
+    }
+    k_build_doc_rows<<<grid, wpc * 32, 0, c->stream>>>(cp.D, c->K, cp.d_doc_ptr, cp.d_z, cp.d_row_ptr, cp.d_row_nnz,
+                                                     cp.d_rows, c->d_hist_scratch);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return B200LDA_OK;
+}
+
+// ---- per-sweep pieces ---------------------------------------------------------------------------
 
 int build_tables(b200lda_ctx* c) {
   const float beta_f = (float)c->beta;
@@ -283,16 +431,17 @@ int build_tables(b200lda_ctx* c) {
   return B200LDA_OK;
 }
 
-SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_write, uint32_t sweep) {
+SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* nwk_read, int32_t* nwk_write,
+                         uint32_t sweep) {
   SweepParams p{};
-  p.doc_order = c->d_doc_order;
-  p.doc_ptr = c->d_doc_ptr;
-  p.tok_word = c->d_tok_word;
-  p.z = c->d_z;
+  p.doc_order = cp.d_doc_order;
+  p.doc_ptr = cp.d_doc_ptr;
+  p.tok_word = cp.d_tok_word;
+  p.z = cp.d_z;
   p.z_out = nullptr;
-  p.row_ptr = c->d_row_ptr;
-  p.row_nnz = c->d_row_nnz;
-  p.rows = c->d_rows;
+  p.row_ptr = cp.d_row_ptr;
+  p.row_nnz = cp.d_row_nnz;
+  p.rows = cp.d_rows;
   p.nwk_read = nwk_read;
   p.nwk_write = nwk_write;
   p.nk_delta = c->d_nk_delta;
@@ -303,6 +452,7 @@ SweepParams sweep_params(b200lda_ctx* c, const int32_t* nwk_read, int32_t* nwk_w
   p.uniforms = nullptr;
   p.layout = c->layout;
   p.K = c->K;
+  p.exclude_self = 1;
   p.beta_f = (float)c->beta;
   p.seed = c->cfg.seed;
   p.sweep = sweep;
@@ -322,7 +472,8 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
   const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
-  const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
+  const int ctas = (int)std::max<int64_t>(
+      1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
   if (sh.tables_in_smem)
     k_gibbs_sweep<MODE, LIVE, true><<<ctas, sh.warps_per_cta * 32, sh.smem, c->stream>>>(p);
   else
@@ -332,13 +483,13 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   return B200LDA_OK;
 }
 
-// One sweep = the long-document class first (few, long-running warps), then the bulk.
+// One pass over a corpus = the long-row class first (few, long-running warps), then the bulk.
 template <int MODE, bool LIVE>
-int launch_sweep(b200lda_ctx* c, const SweepParams& p) {
+int launch_sweep(b200lda_ctx* c, const DeviceCorpus& cp, const SweepParams& p) {
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
   CU(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->stream));
-  TRY((launch_class<MODE, LIVE>(c, p, c->shape_long, 0, c->n_long, c->d_counters + 0)));
-  TRY((launch_class<MODE, LIVE>(c, p, c->shape_short, c->n_long, c->D, c->d_counters + 8)));
+  TRY((launch_class<MODE, LIVE>(c, p, cp.shape_long, 0, cp.n_long, c->d_counters + 0)));
+  TRY((launch_class<MODE, LIVE>(c, p, cp.shape_short, cp.n_long, cp.D, c->d_counters + 8)));
   return B200LDA_OK;
 }
 
@@ -379,6 +530,7 @@ int need_ready(b200lda_ctx* c) {
   if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
   if (!c->assigned) return fail(B200LDA_ESTATE, "no topic assignments (call b200lda_init_assignments)");
   if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  if (c->in_sync) return fail(B200LDA_ESTATE, "b200lda_counts_sync_begin without b200lda_counts_sync_end");
   return B200LDA_OK;
 }
 
@@ -422,11 +574,13 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
     cudaGetLastError();
     return fail(B200LDA_ENODEV, "no CUDA device visible; libb200lda has no CPU fallback");
   }
-  if (cfg->device < 0 || cfg->device >= ndev) return fail(B200LDA_ENODEV, "device %d out of range (%d visible)", cfg->device, ndev);
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(B200LDA_ENODEV, "device %d out of range (%d visible)", cfg->device, ndev);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10)
-    return fail(B200LDA_ENODEV, "device %d is sm_%d%d; libb200lda is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    return fail(B200LDA_ENODEV, "device %d is sm_%d%d; libb200lda is built for sm_100a only", cfg->device, prop.major,
+                prop.minor);
   CU(cudaSetDevice(cfg->device));
 
   b200lda_ctx* c = new (std::nothrow) b200lda_ctx();
@@ -465,7 +619,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kStatCounters + 1)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
@@ -473,7 +627,9 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   if (multi)
     if ((rc = dev_alloc_t(c, &c->d_exchange, VK + c->K))) return bail(rc);
   if (cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
-      cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * (kStatCounters + 1), c->stream) != cudaSuccess)
+      cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream) != cudaSuccess ||
+      cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
+      cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCounters, c->stream) != cudaSuccess)
     return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
   if ((rc = push_alpha(c))) return bail(rc);
   *out = c;
@@ -484,15 +640,7 @@ void b200lda_destroy(b200lda_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  dev_free(c->d_doc_ptr);
-  dev_free(c->d_tok_word);
-  dev_free(c->d_z);
-  dev_free(c->d_word_ptr);
-  dev_free(c->d_wtok);
-  dev_free(c->d_row_ptr);
-  dev_free(c->d_row_nnz);
-  dev_free(c->d_rows);
-  dev_free(c->d_doc_order);
+  free_corpus(c->corp);
   dev_free(c->d_nwk);
   dev_free(c->d_nwk_b);
   dev_free(c->d_nk);
@@ -519,99 +667,10 @@ void b200lda_destroy(b200lda_ctx* c) {
 
 int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word) {
   TRY(enter(c));
-  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
-  if (num_docs < 0 || !doc_ptr) return fail(B200LDA_EINVAL, "bad corpus arguments");
-  if (doc_ptr[0] != 0) return fail(B200LDA_EINVAL, "doc_ptr[0] must be 0");
-  const int64_t N = doc_ptr[num_docs];
-  if (N > 0 && !tok_word) return fail(B200LDA_EINVAL, "tok_word is null");
-  // host-side packing plan: row capacities min(K, L_d), longest document
-  c->h_doc_ptr.assign(doc_ptr, doc_ptr + num_docs + 1);
-  c->h_row_ptr.resize(num_docs + 1);
-  int max_len = 0;
-  int64_t off = 0;
-  for (int64_t d = 0; d < num_docs; ++d) {
-    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-    if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", (long long)d);
-    if (len > 65535) return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", (long long)d, (long long)len);
-    c->h_row_ptr[d] = off;
-    off += std::min<int64_t>(len, c->K);
-    max_len = std::max<int>(max_len, (int)len);
-  }
-  c->h_row_ptr[num_docs] = off;
-  // visiting order: long-row class first, each class longest document first (counting sort)
-  {
-    const int small = std::min(std::max(32, round_up32(std::min(c->K, std::max(1, max_len)))), c->small_row);
-    std::vector<int64_t> bucket((size_t)max_len + 2, 0);
-    int64_t n_long = 0;
-    for (int64_t d = 0; d < num_docs; ++d) {
-      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-      bucket[(size_t)(max_len - len) + 1]++;  // descending length
-      if (std::min<int64_t>(len, c->K) > small) ++n_long;
-    }
-    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
-    c->h_doc_order.resize((size_t)num_docs);
-    for (int64_t d = 0; d < num_docs; ++d) {
-      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-      c->h_doc_order[(size_t)bucket[(size_t)(max_len - len)]++] = (int32_t)d;
-    }
-    c->n_long = n_long;  // longest-first order puts exactly the long class in front
-  }
+  if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
   c->corpus_loaded = false;
   c->assigned = false;
-  if (num_docs > c->cap_docs) {
-    dev_free(c->d_doc_ptr);
-    dev_free(c->d_row_ptr);
-    dev_free(c->d_row_nnz);
-    dev_free(c->d_doc_order);
-    TRY(dev_alloc_t(c, &c->d_doc_order, (size_t)num_docs));
-    TRY(dev_alloc_t(c, &c->d_doc_ptr, (size_t)num_docs + 1));
-    TRY(dev_alloc_t(c, &c->d_row_ptr, (size_t)num_docs + 1));
-    TRY(dev_alloc_t(c, &c->d_row_nnz, (size_t)num_docs));
-    c->cap_docs = num_docs;
-  }
-  if (N > c->cap_tokens) {
-    dev_free(c->d_tok_word);
-    dev_free(c->d_z);
-    dev_free(c->d_wtok);
-    TRY(dev_alloc_t(c, &c->d_tok_word, (size_t)N));
-    TRY(dev_alloc_t(c, &c->d_z, (size_t)N));
-    TRY(dev_alloc_t(c, &c->d_wtok, (size_t)N));
-    c->cap_tokens = N;
-  }
-  if (off > c->cap_rows) {
-    dev_free(c->d_rows);
-    TRY(dev_alloc_t(c, &c->d_rows, (size_t)off));
-    c->cap_rows = off;
-  }
-  if (!c->d_word_ptr) TRY(dev_alloc_t(c, &c->d_word_ptr, (size_t)c->V + 1));
-  c->D = num_docs;
-  c->N = N;
-  c->max_doc_len = max_len;
-  CU(cudaMemcpyAsync(c->d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_row_ptr, c->h_row_ptr.data(), sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
-  if (num_docs > 0)
-    CU(cudaMemcpyAsync(c->d_doc_order, c->h_doc_order.data(), sizeof(int32_t) * num_docs, cudaMemcpyHostToDevice, c->stream));
-  if (N > 0) CU(cudaMemcpyAsync(c->d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
-  // word -> token CSR by counting sort; the histogram pass also validates word ids
-  TRY(ensure_stage(c, sizeof(unsigned long long) * (size_t)c->V));
-  unsigned long long* d_wcount = reinterpret_cast<unsigned long long*>(c->d_stage);
-  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
-  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
-  if (N > 0) k_word_hist<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, c->d_tok_word, d_wcount, c->d_bad);
-  k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>(c->V, d_wcount, c->d_word_ptr);
-  c->launches += 2;
-  int bad = 0;
-  CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (bad) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
-  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
-  if (N > 0) {
-    k_word_scatter<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->d_tok_word, c->d_word_ptr, d_wcount, c->d_wtok);
-    c->launches += 1;
-  }
-  CU(cudaGetLastError());
-  TRY(configure_sweep(c));
-  CU(cudaStreamSynchronize(c->stream));
+  TRY(pack_corpus(c, c->corp, num_docs, doc_ptr, tok_word, true));
   c->corpus_loaded = true;
   return B200LDA_OK;
 }
@@ -619,59 +678,63 @@ int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr
 int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
   TRY(enter(c));
   if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
-  if (c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_begin without b200lda_sweep_end");
+  if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
   c->assigned = false;
-  const int64_t N = c->N;
+  DeviceCorpus& cp = c->corp;
+  const int64_t N = cp.N;
   if (N > 0) {
     if (z) {
       TRY(ensure_stage(c, sizeof(int32_t) * (size_t)N));
       CU(cudaMemcpyAsync(c->d_stage, z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
       k_narrow_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, reinterpret_cast<const int32_t*>(c->d_stage),
-                                                          c->d_z, c->d_bad);
+                                                          cp.d_z, c->d_bad);
       int bad = 0;
       CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       if (bad) return fail(B200LDA_ERANGE, "z holds a topic outside [0, %d)", c->K);
     } else {
-      k_init_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, c->cfg.seed, c->cfg.global_token_offset, c->d_z);
+      k_init_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, c->cfg.seed, c->cfg.global_token_offset, cp.d_z);
     }
     c->launches += 1;
   }
-  // n_wk, n_k from the word -> token order
+  // n_wk from the word -> token order, n_k as its column sums
   const size_t VK = (size_t)c->V * c->K;
   CU(cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream));
   CU(cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream));
   CU(cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream));
   if (N > 0) {
-    k_count_by_word<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_word_ptr, c->d_wtok,
-                                                                                c->d_z, c->d_nwk, c->d_nk);
-    c->launches += 1;
+    k_count_sorted<<<grid_for(c, N, 256, 16), 256, 0, c->stream>>>(N, c->K, cp.d_wtok, cp.d_tok_word, cp.d_z, c->d_nwk);
+    const int rows_per_block = 256;
+    dim3 grid((c->K + 255) / 256, (c->V + rows_per_block - 1) / rows_per_block);
+    k_col_sums<<<grid, 256, 0, c->stream>>>(c->V, c->K, rows_per_block, c->d_nwk, c->d_nk);
+    c->launches += 2;
   }
-  // sparse doc-topic rows
-  if (c->D > 0) {
-    const int wpc = 8;
-    const size_t hist_smem = sizeof(uint32_t) * (size_t)c->K * wpc;
-    const int grid = grid_for(c, c->D * 32, 256, hist_smem <= 48 * 1024 ? 8 : 2);
-    if (hist_smem <= 96 * 1024) {
-      CU(cudaFuncSetAttribute(k_build_doc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-      k_build_doc_rows<<<grid, wpc * 32, hist_smem, c->stream>>>(c->D, c->K, c->d_doc_ptr, c->d_z, c->d_row_ptr,
-                                                               c->d_row_nnz, c->d_rows, nullptr);
-    } else {
-      const size_t need = sizeof(uint32_t) * (size_t)c->K * wpc * grid;
-      if (need > c->hist_scratch_bytes) {
-        dev_free(c->d_hist_scratch);
-        TRY(dev_alloc(c, reinterpret_cast<void**>(&c->d_hist_scratch), need));
-        c->hist_scratch_bytes = need;
-      }
-      k_build_doc_rows<<<grid, wpc * 32, 0, c->stream>>>(c->D, c->K, c->d_doc_ptr, c->d_z, c->d_row_ptr, c->d_row_nnz,
-                                                       c->d_rows, c->d_hist_scratch);
-    }
-    c->launches += 1;
-  }
+  TRY(build_doc_rows(c, cp));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->assigned = true;
+  return B200LDA_OK;
+}
+
+int b200lda_counts_sync_begin(b200lda_ctx* c) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!c->d_exchange) return fail(B200LDA_ESTATE, "count sync needs world_size > 1");
+  const size_t VK = (size_t)c->V * c->K;
+  CU(cudaMemcpyAsync(c->d_exchange, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_exchange + VK, c->d_nk, sizeof(int32_t) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  c->in_sync = true;
+  return B200LDA_OK;
+}
+
+int b200lda_counts_sync_end(b200lda_ctx* c) {
+  TRY(enter(c));
+  if (!c->in_sync) return fail(B200LDA_ESTATE, "b200lda_counts_sync_end without b200lda_counts_sync_begin");
+  const size_t VK = (size_t)c->V * c->K;
+  CU(cudaMemcpyAsync(c->d_nwk, c->d_exchange, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_nk, c->d_exchange + VK, sizeof(int32_t) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  c->in_sync = false;
   return B200LDA_OK;
 }
 
@@ -689,11 +752,11 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
     CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
   // DEFERRED: read the frozen d_nwk, write moves into the copy d_nwk_b.
   // LIVE:     read and write d_nwk in place (d_nwk_b keeps the sweep-start snapshot if multi).
-  SweepParams p = sweep_params(c, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
+  SweepParams p = sweep_params(c, c->corp, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
   if (deferred)
-    TRY((launch_sweep<MODE_UPDATE, false>(c, p)));
+    TRY((launch_sweep<MODE_UPDATE, false>(c, c->corp, p)));
   else
-    TRY((launch_sweep<MODE_UPDATE, true>(c, p)));
+    TRY((launch_sweep<MODE_UPDATE, true>(c, c->corp, p)));
   CU(cudaEventRecord(c->ev[2], c->stream));
   if (multi) {
     const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;
@@ -734,7 +797,7 @@ int b200lda_sweep_end(b200lda_ctx* c) {
   c->ev_pending += 1;
   c->in_sweep = false;
   c->sweeps_done += 1;
-  c->tokens_sampled += c->N;
+  c->tokens_sampled += c->corp.N;
   return B200LDA_OK;
 }
 
@@ -768,35 +831,94 @@ int b200lda_sample_frozen(b200lda_ctx* c, const float* uniforms, uint32_t sweep,
   TRY(enter(c));
   TRY(need_ready(c));
   if (!z_out) return fail(B200LDA_EINVAL, "z_out is null");
-  const int64_t N = c->N;
+  const int64_t N = c->corp.N;
   if (N == 0) return B200LDA_OK;
   TRY(ensure_stage(c, (size_t)N * 8));
   int32_t* d_zout = reinterpret_cast<int32_t*>(c->d_stage);
   float* d_u = reinterpret_cast<float*>(c->d_stage) + N;
   if (uniforms) CU(cudaMemcpyAsync(d_u, uniforms, sizeof(float) * N, cudaMemcpyHostToDevice, c->stream));
   TRY(build_tables(c));
-  SweepParams p = sweep_params(c, c->d_nwk, c->d_nwk_b ? c->d_nwk_b : c->d_nwk, sweep);
-  // distinct read/write pointers => read-only cached loads; MODE_FROZEN never writes counts
-  p.nwk_write = nullptr;
+  SweepParams p = sweep_params(c, c->corp, c->d_nwk, nullptr, sweep);  // MODE_FROZEN never writes counts
   p.z_out = d_zout;
   p.uniforms = uniforms ? d_u : nullptr;
-  TRY((launch_sweep<MODE_FROZEN, false>(c, p)));
+  TRY((launch_sweep<MODE_FROZEN, false>(c, c->corp, p)));
   CU(cudaMemcpyAsync(z_out, d_zout, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
+}
+
+int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word, int32_t iterations,
+                  int32_t thinning, int32_t burn_in, uint64_t seed, double* theta) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (num_docs < 0 || !doc_ptr || (num_docs > 0 && !theta)) return fail(B200LDA_EINVAL, "bad inference arguments");
+  if (iterations < 0 || thinning < 1 || burn_in < 0) return fail(B200LDA_EINVAL, "bad iterations/thinning/burn-in");
+  if (num_docs == 0) return B200LDA_OK;
+  // held-out documents are packed like a corpus of their own; the trained counts stay frozen
+  DeviceCorpus cp;
+  const int64_t bytes_before = c->device_bytes;
+  int rc = pack_corpus(c, cp, num_docs, doc_ptr, tok_word, false);
+  int32_t* d_acc = nullptr;
+  double* d_theta = nullptr;
+  auto cleanup = [&](int code) {
+    cudaStreamSynchronize(c->stream);
+    free_corpus(cp);
+    dev_free(d_acc);
+    dev_free(d_theta);
+    c->device_bytes = bytes_before;
+    return code;
+  };
+  if (rc) return cleanup(rc);
+  const size_t DK = (size_t)num_docs * c->K;
+  if ((rc = dev_alloc_t(c, &d_acc, DK)) || (rc = dev_alloc_t(c, &d_theta, DK))) return cleanup(rc);
+  if (cudaMemsetAsync(d_acc, 0, sizeof(int32_t) * DK, c->stream) != cudaSuccess) return cleanup(fail(B200LDA_ECUDA, "memset failed"));
+  if (cp.N > 0)  // TopicInferencer: uniform random initial topics (own Philox stream: sweep 0, seed-keyed)
+    k_init_z<<<grid_for(c, cp.N, 256), 256, 0, c->stream>>>(cp.N, c->K, seed ^ 0x9E3779B97F4A7C15ull, 0, cp.d_z);
+  if ((rc = build_doc_rows(c, cp))) return cleanup(rc);
+  if ((rc = build_tables(c))) return cleanup(rc);
+  int samples = 0;
+  for (int32_t it = 1; it <= iterations; ++it) {
+    SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, (uint32_t)it);
+    p.exclude_self = 0;  // the held-out tokens are not part of n_wk / n_k
+    p.stats_cum = c->d_counters + 9;
+    p.seed = seed;
+    p.global_tok_off = 0;
+    if ((rc = launch_sweep<MODE_UPDATE, false>(c, cp, p))) return cleanup(rc);
+    if (it > burn_in && (it - burn_in) % thinning == 0) {
+      k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
+                                                                             cp.d_rows, d_acc);
+      c->launches += 1;
+      ++samples;
+    }
+  }
+  if (samples == 0) {  // Mallet: no sample saved -> use the final state
+    k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
+                                                                           cp.d_rows, d_acc);
+    samples = 1;
+  }
+  k_infer_theta<<<grid_for(c, (int64_t)DK, 256), 256, 0, c->stream>>>(num_docs, c->K, samples, cp.d_doc_ptr, d_acc, c->d_alpha,
+                                                                     c->alpha_sum, d_theta);
+  c->launches += 2;
+  if (cudaGetLastError() != cudaSuccess) return cleanup(fail(B200LDA_ECUDA, "inference kernel launch failed"));
+  if (cudaMemcpyAsync(theta, d_theta, sizeof(double) * DK, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return cleanup(fail(B200LDA_ECUDA, "inference copy-back failed: %s", cudaGetErrorString(cudaGetLastError())));
+  // inference must not disturb the training chain's n_k delta accumulator or stats of the last sweep
+  return cleanup(B200LDA_OK);
 }
 
 int b200lda_loglik_parts(b200lda_ctx* c, double* doc_part, double* word_part) {
   TRY(enter(c));
   TRY(need_ready(c));
   if (!doc_part || !word_part) return fail(B200LDA_EINVAL, "null argument");
+  const DeviceCorpus& cp = c->corp;
   const size_t VK = (size_t)c->V * c->K;
   double* p_docs = c->d_partial;
   double* p_words = c->d_partial + kPartial;
   double* d_out = c->d_partial + 2 * kPartial;
   unsigned long long* d_nz = c->d_counters + 4;
   CU(cudaMemsetAsync(d_nz, 0, sizeof(unsigned long long), c->stream));
-  k_loglik_docs<<<kPartial, 256, 0, c->stream>>>(c->D, c->d_doc_ptr, c->d_row_ptr, c->d_row_nnz, c->d_rows, c->d_alpha,
+  k_loglik_docs<<<kPartial, 256, 0, c->stream>>>(cp.D, cp.d_doc_ptr, cp.d_row_ptr, cp.d_row_nnz, cp.d_rows, c->d_alpha,
                                                 c->d_lg_alpha, c->alpha_sum, p_docs);
   k_loglik_words<<<kPartial, 256, 0, c->stream>>>(VK, c->d_nwk, c->beta, p_words, d_nz);
   k_loglik_final<<<1, 256, 0, c->stream>>>(kPartial, p_docs, 0, c->d_nk, 0.0, d_out + 0);
@@ -808,7 +930,7 @@ int b200lda_loglik_parts(b200lda_ctx* c, double* doc_part, double* word_part) {
   CU(cudaMemcpyAsync(h, d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(&nz, d_nz, sizeof(nz), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  *doc_part = h[0] + (double)c->D * std::lgamma(c->alpha_sum);
+  *doc_part = h[0] + (double)cp.D * std::lgamma(c->alpha_sum);
   *word_part = h[1] + (double)c->K * std::lgamma(c->beta * (double)c->V) - (double)nz * std::lgamma(c->beta);
   return B200LDA_OK;
 }
@@ -825,11 +947,11 @@ int b200lda_get_assignments(b200lda_ctx* c, int32_t* z) {
   TRY(enter(c));
   TRY(need_ready(c));
   if (!z) return fail(B200LDA_EINVAL, "z is null");
-  const int64_t N = c->N;
+  const int64_t N = c->corp.N;
   if (N == 0) return B200LDA_OK;
   TRY(ensure_stage(c, sizeof(int32_t) * (size_t)N));
   int32_t* d_wide = reinterpret_cast<int32_t*>(c->d_stage);
-  k_widen_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->d_z, d_wide);
+  k_widen_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->corp.d_z, d_wide);
   c->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(z, d_wide, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
@@ -859,18 +981,19 @@ int b200lda_get_ndk_csr(b200lda_ctx* c, int64_t* row_ptr, int32_t* topic, int32_
   TRY(enter(c));
   TRY(need_ready(c));
   if (!row_ptr) return fail(B200LDA_EINVAL, "row_ptr is null");
-  std::vector<int32_t> nnz((size_t)c->D);
-  if (c->D > 0) CU(cudaMemcpyAsync(nnz.data(), c->d_row_nnz, sizeof(int32_t) * c->D, cudaMemcpyDeviceToHost, c->stream));
+  const DeviceCorpus& cp = c->corp;
+  std::vector<int32_t> nnz((size_t)cp.D);
+  if (cp.D > 0) CU(cudaMemcpyAsync(nnz.data(), cp.d_row_nnz, sizeof(int32_t) * cp.D, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   row_ptr[0] = 0;
-  for (int64_t d = 0; d < c->D; ++d) row_ptr[d + 1] = row_ptr[d] + nnz[d];
+  for (int64_t d = 0; d < cp.D; ++d) row_ptr[d + 1] = row_ptr[d] + nnz[d];
   if (!topic || !count) return B200LDA_OK;
-  const int64_t cap = c->h_row_ptr[c->D];
+  const int64_t cap = cp.h_row_ptr[cp.D];
   std::vector<uint32_t> rows((size_t)cap);
-  if (cap > 0) CU(cudaMemcpyAsync(rows.data(), c->d_rows, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, c->stream));
+  if (cap > 0) CU(cudaMemcpyAsync(rows.data(), cp.d_rows, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  for (int64_t d = 0; d < c->D; ++d) {
-    const uint32_t* src = rows.data() + c->h_row_ptr[d];
+  for (int64_t d = 0; d < cp.D; ++d) {
+    const uint32_t* src = rows.data() + cp.h_row_ptr[d];
     for (int32_t j = 0; j < nnz[d]; ++j) {
       topic[row_ptr[d] + j] = (int32_t)(src[j] >> 16);
       count[row_ptr[d] + j] = (int32_t)(src[j] & 0xffffu);
@@ -882,7 +1005,8 @@ int b200lda_get_ndk_csr(b200lda_ctx* c, int64_t* row_ptr, int32_t* topic, int32_
 int b200lda_get_theta(b200lda_ctx* c, int64_t doc_begin, int64_t doc_end, double* theta) {
   TRY(enter(c));
   TRY(need_ready(c));
-  if (doc_begin < 0 || doc_end > c->D || doc_begin > doc_end) return fail(B200LDA_EINVAL, "bad document range");
+  const DeviceCorpus& cp = c->corp;
+  if (doc_begin < 0 || doc_end > cp.D || doc_begin > doc_end) return fail(B200LDA_EINVAL, "bad document range");
   if (doc_begin == doc_end) return B200LDA_OK;
   if (!theta) return fail(B200LDA_EINVAL, "theta is null");
   const int64_t chunk = std::max<int64_t>(1, (int64_t)(256u << 20) / (int64_t)(sizeof(double) * c->K));
@@ -890,8 +1014,8 @@ int b200lda_get_theta(b200lda_ctx* c, int64_t doc_begin, int64_t doc_end, double
     const int64_t d1 = std::min(doc_end, d0 + chunk);
     TRY(ensure_stage(c, sizeof(double) * (size_t)(d1 - d0) * c->K));
     double* d_theta = reinterpret_cast<double*>(c->d_stage);
-    k_theta<<<grid_for(c, (d1 - d0) * 32, 256), 256, 0, c->stream>>>(d0, d1, c->K, c->d_doc_ptr, c->d_row_ptr, c->d_row_nnz,
-                                                                    c->d_rows, c->d_alpha, c->alpha_sum, d_theta);
+    k_theta<<<grid_for(c, (d1 - d0) * 32, 256), 256, 0, c->stream>>>(d0, d1, c->K, cp.d_doc_ptr, cp.d_row_ptr, cp.d_row_nnz,
+                                                                    cp.d_rows, c->d_alpha, c->alpha_sum, d_theta);
     c->launches += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(theta + (size_t)(d0 - doc_begin) * c->K, d_theta, sizeof(double) * (size_t)(d1 - d0) * c->K,
@@ -957,19 +1081,19 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   if (!out) return fail(B200LDA_EINVAL, "null argument");
   memset(out, 0, sizeof(*out));
   CU(cudaStreamSynchronize(c->stream));
-  out->num_docs = c->D;
-  out->num_tokens = c->N;
+  out->num_docs = c->corp.D;
+  out->num_tokens = c->corp.N;
   out->sweeps_done = c->sweeps_done;
   out->kernel_launches = c->launches;
   out->tokens_sampled = c->tokens_sampled;
   out->device_bytes = c->device_bytes;
-  out->smem_bytes_per_cta = (int32_t)c->shape_short.smem;
-  out->warps_per_cta = c->shape_short.warps_per_cta;
-  out->ctas = c->shape_short.ctas;
-  out->slot_capacity = c->shape_short.slot_cap;
-  out->long_docs = c->n_long;
-  out->long_slot_capacity = c->shape_long.slot_cap;
-  out->long_ctas = c->shape_long.ctas;
+  out->smem_bytes_per_cta = (int32_t)c->corp.shape_short.smem;
+  out->warps_per_cta = c->corp.shape_short.warps_per_cta;
+  out->ctas = c->corp.shape_short.ctas;
+  out->slot_capacity = c->corp.shape_short.slot_cap;
+  out->long_docs = c->corp.n_long;
+  out->long_slot_capacity = c->corp.shape_long.slot_cap;
+  out->long_ctas = c->corp.shape_long.ctas;
   if (c->in_sweep) return B200LDA_OK;  // timings of an open sweep are not resolvable yet
   TRY(resolve_events(c));
   out->last_tables_ms = c->last_tables_ms;
@@ -980,11 +1104,11 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->cum_tables_ms = c->cum_tables_ms;
   out->cum_sample_ms = c->cum_sample_ms;
   out->cum_finish_ms = c->cum_finish_ms;
-  unsigned long long h[kStatCounters];
+  unsigned long long h[kCounters];
   CU(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
   out->tokens_moved_last = (int64_t)h[1];
   out->prior_bucket_last = (int64_t)h[2];
-  out->mean_doc_topics = c->N > 0 ? (double)h[3] / (double)c->N : 0.0;
+  out->mean_doc_topics = c->corp.N > 0 ? (double)h[3] / (double)c->corp.N : 0.0;
   out->cum_tokens_moved = (int64_t)h[5];
   out->cum_prior_bucket = (int64_t)h[6];
   out->cum_doc_topics = (int64_t)h[7];

@@ -114,6 +114,37 @@ k_theta(int64_t d0, int64_t d1, int K, const int64_t* __restrict__ doc_ptr, cons
   }
 }
 
+// Held-out inference (TopicInferencer.getSampledDistribution): acc[d, k] += n_dk of the current
+// sample; theta follows as (S alpha_k + acc) / (S (sum alpha + L_d)) after S samples.
+__global__ void __launch_bounds__(256)
+k_infer_accumulate(int64_t D, int K, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ row_nnz,
+                   const uint32_t* __restrict__ rows, int32_t* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t d = gw; d < D; d += nw) {
+    const int64_t rp = row_ptr[d];
+    const int n = row_nnz[d];
+    for (int j = lane; j < n; j += 32) {
+      const uint32_t s = rows[rp + j];
+      acc[(size_t)d * K + (s >> 16)] += (int32_t)(s & 0xffffu);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_infer_theta(int64_t D, int K, int samples, const int64_t* __restrict__ doc_ptr, const int32_t* __restrict__ acc,
+              const double* __restrict__ alpha, double alpha_sum, double* __restrict__ theta) {
+  const size_t total = (size_t)D * K;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t d = (int64_t)(i / K);
+    const int k = (int)(i % K);
+    const double len = (double)(doc_ptr[d + 1] - doc_ptr[d]);
+    theta[i] = ((double)samples * alpha[k] + (double)acc[i]) / ((double)samples * (alpha_sum + len));
+  }
+}
+
 // phi[k, w] = (n_wk + beta) / (n_k + V beta) for topics [k0, k1): 32x32 shared-memory transpose
 // so both the n_wk reads (row = word) and the phi writes (row = topic) are coalesced.
 __global__ void __launch_bounds__(256)

@@ -105,22 +105,27 @@ __global__ void k_word_scatter(int64_t N, const int32_t* __restrict__ tok_word, 
   }
 }
 
-// n_wk rows from the word -> token order: one warp per word gathers its tokens' topics and
-// accumulates the row with shared-memory-free integer atomics on its own (L2-resident) row.
+// n_wk from the word -> token order: consecutive threads touch the same / neighbouring n_wk rows,
+// so the integer atomics stay in L2 and a frequent word is spread over many warps.
 __global__ void __launch_bounds__(256)
-k_count_by_word(int V, int K, const long long* __restrict__ word_ptr, const int64_t* __restrict__ wtok,
-                const uint16_t* __restrict__ z, int32_t* __restrict__ nwk, int32_t* __restrict__ nk) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t w = gw; w < V; w += nw) {
-    const long long b = word_ptr[w], e = word_ptr[w + 1];
-    int32_t* row = nwk + (size_t)w * K;
-    for (long long i = b + lane; i < e; i += 32) {
-      const int k = (int)z[wtok[i]];
-      atomicAdd(row + k, 1);
-      atomicAdd(nk + k, 1);
-    }
+k_count_sorted(int64_t N, int K, const int64_t* __restrict__ wtok, const int32_t* __restrict__ tok_word,
+               const uint16_t* __restrict__ z, int32_t* __restrict__ nwk) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int64_t t = wtok[i];
+    atomicAdd(nwk + (size_t)tok_word[t] * K + z[t], 1);
+  }
+}
+
+// n_k = column sums of n_wk: each block reduces a slab of rows, one thread per topic column.
+__global__ void __launch_bounds__(256)
+k_col_sums(int V, int K, int rows_per_block, const int32_t* __restrict__ nwk, int32_t* __restrict__ nk) {
+  const int w0 = blockIdx.y * rows_per_block;
+  const int w1 = min(V, w0 + rows_per_block);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    int acc = 0;
+    for (int w = w0; w < w1; ++w) acc += nwk[(size_t)w * K + k];
+    if (acc) atomicAdd(nk + k, acc);
   }
 }
 

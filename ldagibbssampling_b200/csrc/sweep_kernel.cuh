@@ -48,6 +48,8 @@ struct SweepParams {
   int K;
   int slot_cap;               // shared-memory slots per warp (multiple of 32)
   int doc_chunk;              // documents fetched per scheduler atomic
+  int exclude_self;           // 1: the token being resampled is counted in n_wk (training);
+                              // 0: held-out inference against frozen counts (TopicInferencer)
   float beta_f;
   uint64_t seed;
   uint32_t sweep;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
                 const unsigned bo = __ballot_sync(kFullMask, is_old);
                 if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
                 const int c = (int)(sv[g] & 0xffffu) - (int)is_old;
-                const int n = max(nv[g] - (int)is_old, 0);
+                const int n = max(nv[g] - ((int)is_old & p.exclude_self), 0);
                 const float inv = TABLES_IN_SMEM ? s_tab[topic] : __ldg(p.invden + topic);
                 float a = fmul(fmul(fadd((float)n, beta_f), inv), (float)c);  // c == 0 past nnz
                 a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), m1, a);
@@ -197,7 +199,8 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
             }
           }
           const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
-          const float delta = TABLES_IN_SMEM ? s_tab[K + o] : __ldg(p.ab + o);
+          float delta = TABLES_IN_SMEM ? s_tab[K + o] : __ldg(p.ab + o);
+          delta = p.exclude_self ? delta : 0.0f;
           float qp = fsub(qw, delta);
           qp = qp < 0.0f ? 0.0f : qp;
           const float T = fadd(A, qp);
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
             }
             __syncwarp();
             // word-topic and topic totals: integer RED atomics (order-independent sums)
-            if (lane == 0) {
+            if (lane == 0 && p.nwk_write != nullptr) {
               int32_t* wrow = p.nwk_write + (size_t)w * K;
               atomicAdd(wrow + o, -1);
               atomicAdd(wrow + newt, 1);

@@ -1,0 +1,421 @@
+"""Host-side mirror of the Mallet entry points the reference drives, over the C ABI.
+
+Same names, argument meaning and error behaviour as the used subset of
+cc.mallet.topics.ParallelTopicModel / TopicInferencer, so the reference's
+trainNewModel (cmu_ron/TrainAndPredict.java:159-171, cmu/TrainAndPredict.java:258-269) reads the
+same with `ParallelTopicModel` imported from here:
+
+    model = ParallelTopicModel(500, 100, 1)      # K, alphaSum (NOT alpha), beta
+    model.addInstances(training)
+    model.setOptimizeInterval(20); model.setNumThreads(4); model.setNumIterations(10000)
+    model.estimate()
+    inferencer = model.getInferencer()
+
+All arithmetic happens in libb200lda.so on the GPU; there is no CPU fallback. setNumThreads(n)
+means n AD-LDA shards = n GPUs (one context each; under torch.distributed one rank = one shard).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional
+
+import numpy as np
+
+from . import _capi
+from .instances import Alphabet, FeatureSequence, Instance, InstanceList, LabelSequence, TopicAssignment
+from .partition import partition_by_tokens, shard_corpus
+
+
+class _LocalReducer:
+    """Sums the shards' exchange buffers when every shard lives in this process (several contexts,
+    one per GPU or several per GPU). Device-side adds through torch; no host round trip."""
+
+    def __init__(self, samplers):
+        import torch
+        self.torch = torch
+        self.bufs = []
+        for s in samplers:
+            ptr, n = s.exchange_buffer()
+            dev = torch.device("cuda", s.device)
+            self.bufs.append(torch.as_tensor(_DevBuf(ptr, n), device=dev))
+
+    def __call__(self, samplers):
+        torch = self.torch
+        for s in samplers:
+            s.synchronize()
+        total = self.bufs[0]
+        for b in self.bufs[1:]:
+            total += b.to(total.device)
+        for b in self.bufs[1:]:
+            b.copy_(total)
+        for b in self.bufs:
+            torch.cuda.synchronize(b.device)
+
+
+class _DevBuf:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+
+class _DistReducer:
+    """One process per GPU: the exchange is a torch.distributed all-reduce (NCCL over NVLink)
+    enqueued on the sampler's stream between sweep_begin and sweep_end."""
+
+    def __init__(self, sampler, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        ptr, n = sampler.exchange_buffer()
+        self.buf = torch.as_tensor(_DevBuf(ptr, n), device=torch.device("cuda", sampler.device))
+        self.stream = torch.cuda.ExternalStream(sampler.stream(), device=torch.device("cuda", sampler.device))
+
+    def __call__(self, samplers):
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_reduce(self.buf, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class ParallelTopicModel:
+    """Mirror of cc.mallet.topics.ParallelTopicModel (the subset the reference calls)."""
+
+    DEFAULT_BETA = 0.01
+
+    def __init__(self, numberOfTopics: int, alphaSum: Optional[float] = None, beta: float = DEFAULT_BETA):
+        if numberOfTopics < 1:
+            raise ValueError("numberOfTopics must be >= 1")
+        self.numTopics = int(numberOfTopics)
+        self.alphaSum = float(numberOfTopics if alphaSum is None else alphaSum)  # Mallet: (K) -> alphaSum = K
+        self.alpha = np.full(self.numTopics, self.alphaSum / self.numTopics, np.float64)
+        self.beta = float(beta)
+        self.data: List[TopicAssignment] = []
+        self.alphabet: Optional[Alphabet] = None
+        self.numTypes = 0
+        self.betaSum = 0.0
+        # Mallet defaults
+        self.numIterations = 1000
+        self.burninPeriod = 200
+        self.optimizeInterval = 50
+        self.showTopicsInterval = 50
+        self.wordsPerTopic = 7
+        self.numThreads = 1
+        self.randomSeed = -1
+        # B200 specifics
+        self.mode = _capi.MODE_LIVE
+        self.devices: Optional[List[int]] = None      # one entry per shard; default 0..numThreads-1
+        self.distributed = False                      # True: this process is ONE shard of a torch.distributed job
+        self.process_group = None
+        self._samplers: List[_capi.Sampler] = []
+        self._shards = []
+        self._iterationsSoFar = 0
+        self._dirty = True        # instances added since the device state was built
+        self._z_host: Optional[np.ndarray] = None
+        self._doc_ptr = np.zeros(1, np.int64)
+        self._tok = np.zeros(0, np.int32)
+
+    # -- configuration (same names as Mallet) -------------------------------------------------
+    def setNumIterations(self, n: int):
+        self.numIterations = int(n)
+
+    def setBurninPeriod(self, n: int):
+        self.burninPeriod = int(n)
+
+    def setOptimizeInterval(self, n: int):
+        self.optimizeInterval = int(n)
+
+    def setNumThreads(self, n: int):
+        self.numThreads = max(1, int(n))
+
+    def setRandomSeed(self, seed: int):
+        self.randomSeed = int(seed)
+
+    def setTopicDisplay(self, interval: int, n: int):
+        self.showTopicsInterval = int(interval)
+        self.wordsPerTopic = int(n)
+
+    def setSamplingMode(self, mode):
+        """B200 extension: 'live' (default) or 'deferred' (bit-reproducible, shard-count independent)."""
+        self.mode = {"live": _capi.MODE_LIVE, "deferred": _capi.MODE_DEFERRED}.get(mode, mode)
+        self._dirty = True
+
+    def setDevices(self, devices):
+        self.devices = list(devices)
+        self._dirty = True
+
+    def setDistributed(self, flag: bool = True, group=None):
+        self.distributed = bool(flag)
+        self.process_group = group
+        self._dirty = True
+
+    def getAlphabet(self) -> Alphabet:
+        return self.alphabet
+
+    def getData(self):
+        return self.data
+
+    def getNumTopics(self) -> int:
+        return self.numTopics
+
+    # -- addInstances ---------------------------------------------------------------------------
+    def addInstances(self, training: InstanceList):
+        """Takes the documents (FeatureSequences over one alphabet), draws the initial topics and
+        builds the counts. May be called again with more documents (the reference's updateModel,
+        cmu_ron/TrainAndPredict.java:173-177): existing assignments are kept."""
+        alphabet = training.getDataAlphabet()
+        if self.alphabet is None:
+            self.alphabet = alphabet
+        elif alphabet is not self.alphabet:
+            raise ValueError("instances must share the model's data alphabet")
+        self._pull_assignments()          # keep the chain state of documents already in the model
+        doc_ptr, tok = training.flatten()
+        if len(tok) and int(np.diff(doc_ptr).max()) > 65535:
+            raise ValueError("a document is longer than 65535 tokens")
+        old_n = len(self._tok)
+        self._doc_ptr = np.concatenate([self._doc_ptr, doc_ptr[1:] + self._doc_ptr[-1]])
+        self._tok = np.concatenate([self._tok, tok])
+        for inst in training:
+            self.data.append(TopicAssignment(inst, LabelSequence(np.zeros(inst.getData().getLength(), np.int32))))
+        self.numTypes = self.alphabet.size()
+        self.betaSum = self.beta * self.numTypes
+        self._new_from = old_n
+        self._dirty = True
+        self._build_device_state()
+
+    def _seed(self) -> int:
+        if self.randomSeed == -1:
+            import time
+            self.randomSeed = int(time.time_ns() & 0x7FFFFFFF)   # Mallet: clock-seeded unless setRandomSeed
+        return self.randomSeed
+
+    def _world(self):
+        if self.distributed:
+            import torch.distributed as dist
+            return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        return self.numThreads, None
+
+    def _build_device_state(self):
+        for s in self._samplers:
+            s.close()
+        self._samplers, self._shards = [], []
+        world, my_rank = self._world()
+        shards = partition_by_tokens(self._doc_ptr, world)
+        seed = self._seed()
+        ranks = [my_rank] if my_rank is not None else list(range(world))
+        if my_rank is not None:
+            import torch
+            devices = {my_rank: torch.cuda.current_device()}
+        else:
+            devs = self.devices if self.devices is not None else list(range(world))
+            if len(devs) != world:
+                raise ValueError("setDevices needs one device per thread/shard")
+            devices = dict(zip(ranks, devs))
+        # initial topics of documents that are new to the model come from the device (Philox);
+        # documents already sampled keep their topics
+        for r in ranks:
+            sh = shards[r]
+            dp, tok = shard_corpus(self._doc_ptr, self._tok, sh)
+            s = _capi.Sampler(self.numTopics, max(self.numTypes, 1), self.alphaSum, self.beta, seed=seed,
+                              mode=self.mode, device=devices[r], rank=r, world_size=world,
+                              global_token_offset=sh.token_begin, global_doc_offset=sh.doc_begin)
+            s.set_alpha(self.alpha)
+            s.load_corpus(dp, tok)
+            if self._z_host is None or self._new_from == 0:
+                s.init_assignments(None)
+            else:
+                s.init_assignments(None)
+                z = s.assignments()
+                keep = min(sh.token_end, self._new_from) - sh.token_begin
+                if keep > 0:
+                    z[:keep] = self._z_host[sh.token_begin:sh.token_begin + keep]
+                s.init_assignments(z)
+            s.set_sweep_counter(self._iterationsSoFar)
+            self._samplers.append(s)
+            self._shards.append(sh)
+        self._reducer = None
+        if world > 1:
+            self._sync_global_counts()
+        self._dirty = False
+        self._z_host = None
+        self._push_assignments_to_data()
+
+    def _sync_global_counts(self):
+        """Each shard built n_wk / n_k from its own documents; one all-reduce of the counts makes
+        every replica global (Mallet's sumTypeTopicCounts at start-up)."""
+        for s in self._samplers:
+            s.counts_sync_begin()
+        self._get_reducer()(self._samplers)
+        for s in self._samplers:
+            s.counts_sync_end()
+        for s in self._samplers:
+            s.synchronize()
+
+    def _get_reducer(self):
+        if self._reducer is None:
+            _, my_rank = self._world()
+            self._reducer = (_DistReducer(self._samplers[0], self.process_group) if my_rank is not None
+                             else _LocalReducer(self._samplers))
+        return self._reducer
+
+    # -- estimate ---------------------------------------------------------------------------------
+    def estimate(self):
+        """Runs numIterations sweeps (Mallet's estimate(); declared `throws IOException` there for
+        its state files — nothing here writes files)."""
+        if not self.data:
+            raise RuntimeError("addInstances must be called before estimate")
+        if self._dirty:
+            self._pull_assignments()
+            self._build_device_state()
+        if self.optimizeInterval != 0:
+            warnings.warn("hyper-parameter optimisation (setOptimizeInterval) is not on the GPU path yet; "
+                          "alpha and beta stay fixed (SURVEY.md §8(f) row 2)", RuntimeWarning, stacklevel=2)
+        n = self.numIterations
+        world, my_rank = self._world()
+        if world == 1:
+            self._samplers[0].sweep(n)
+        else:
+            reducer = self._get_reducer()
+            for _ in range(n):
+                for s in self._samplers:
+                    s.sweep_begin()
+                reducer(self._samplers)
+                for s in self._samplers:
+                    s.sweep_end()
+            for s in self._samplers:
+                s.synchronize()
+        self._iterationsSoFar += n
+        self._push_assignments_to_data()
+
+    def _pull_assignments(self):
+        if self._samplers and not self.distributed:
+            self._z_host = np.concatenate([s.assignments() for s in self._samplers]) if self._samplers else None
+
+    def _push_assignments_to_data(self):
+        """Writes z back into every TopicAssignment.topicSequence so `data` consumers
+        (cmu_ron/TrainAndPredict.java:135-143) keep working."""
+        for s, sh in zip(self._samplers, self._shards):
+            z = s.assignments()
+            dp = self._doc_ptr
+            for d in range(sh.doc_begin, sh.doc_end):
+                self.data[d].topicSequence = LabelSequence(z[dp[d] - sh.token_begin:dp[d + 1] - sh.token_begin])
+
+    # -- outputs ------------------------------------------------------------------------------------
+    def getTopicProbabilities(self, topics) -> np.ndarray:
+        """theta = (n_dk + alpha_k) / (L_d + alphaSum). Accepts a LabelSequence (as the reference
+        passes, cmu_ron/TrainAndPredict.java:143) or a document index."""
+        if isinstance(topics, (int, np.integer)):
+            topics = self.data[int(topics)].topicSequence
+        z = topics.getFeatures()
+        counts = np.bincount(z, minlength=self.numTopics).astype(np.float64)
+        return (counts + self.alpha) / (len(z) + self.alpha.sum())
+
+    def getDocumentTopics(self) -> np.ndarray:
+        """All local theta rows computed on the device (D x K)."""
+        return np.concatenate([s.theta() for s in self._samplers], axis=0)
+
+    def modelLogLikelihood(self) -> float:
+        doc = 0.0
+        word = 0.0
+        for s in self._samplers:
+            d, w = s.loglik_parts()
+            doc += d
+            word = w
+        if self.distributed:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([doc], dtype=torch.float64, device=torch.device("cuda", self._samplers[0].device))
+            dist.all_reduce(t, group=self.process_group)
+            doc = float(t.item())
+        return doc + word
+
+    def getTypeTopicCounts(self):
+        """(n_wk [V x K] int32, n_k [K] int32) — the dense form of Mallet's typeTopicCounts / tokensPerTopic."""
+        s = self._samplers[0]
+        return s.nwk(), s.nk()
+
+    def getInferencer(self) -> "TopicInferencer":
+        return TopicInferencer(self)
+
+    def getTopWords(self, numWords: int):
+        nwk, _ = self.getTypeTopicCounts()
+        out = []
+        for k in range(self.numTopics):
+            col = nwk[:, k]
+            # Mallet sorts each topic's types by count descending (ties: by type index, IDSorter)
+            order = np.lexsort((np.arange(len(col)), -col))[:numWords]
+            out.append([self.alphabet.lookupObject(int(w)) for w in order if col[w] > 0])
+        return out
+
+    def printTopWords(self, file, numWords: int, useNewLines: bool):
+        """`topic \\t alpha_k \\t word word ...` per topic (format witnessed by reference
+        data/Topics.java:13-17,40-49)."""
+        words = self.getTopWords(numWords)
+        with _open_for_write(file) as out:
+            for k in range(self.numTopics):
+                if useNewLines:
+                    out.write(f"{k}\t{_fmt(self.alpha[k])}\n")
+                    for w in words[k]:
+                        out.write(f"{w}\n")
+                else:
+                    out.write(f"{k}\t{_fmt(self.alpha[k])}\t" + " ".join(str(w) + " " for w in words[k]).rstrip(" ") + " \n")
+
+    def printDocumentTopics(self, file, threshold: float = 0.0, max: int = -1):
+        """`doc name topic proportion ...` sorted by proportion descending (format witnessed by
+        reference data/Docs.java:21-26,40-52)."""
+        with _open_for_write(file) as out:
+            out.write("#doc source topic proportion ...\n")
+            for d, ta in enumerate(self.data):
+                theta = self.getTopicProbabilities(ta.topicSequence)
+                order = np.lexsort((np.arange(len(theta)), -theta))
+                limit = len(order) if max < 0 else min(max, len(order))
+                src = ta.instance.getSource()   # Mallet 2.0.7 prints the source, "null-source" when absent
+                out.write(f"{d} {src if src is not None else 'null-source'}")
+                for k in order[:limit]:
+                    if theta[k] <= threshold:
+                        break
+                    out.write(f" {int(k)} {repr(float(theta[k]))}")
+                out.write(" \n")
+
+    def close(self):
+        for s in self._samplers:
+            s.close()
+        self._samplers = []
+
+
+class TopicInferencer:
+    """Mirror of cc.mallet.topics.TopicInferencer as the reference uses it:
+    getSampledDistribution(instance, 100, 10, 10) (cmu_ron/TrainAndPredict.java:144,
+    cmu/TrainAndPredict.java:114). A snapshot of the trained n_wk / n_k / alpha / beta; held-out
+    documents are sampled on the GPU against the frozen counts."""
+
+    def __init__(self, model: ParallelTopicModel):
+        self._model = model
+        self.numTopics = model.numTopics
+        self.randomSeed = 0
+
+    def setRandomSeed(self, seed: int):
+        self.randomSeed = int(seed)
+
+    def getSampledDistribution(self, instance: Instance, numIterations: int, thinning: int, burnIn: int) -> np.ndarray:
+        return self.getSampledDistributions([instance], numIterations, thinning, burnIn)[0]
+
+    def getSampledDistributions(self, instances, numIterations: int, thinning: int, burnIn: int) -> np.ndarray:
+        """Batched form: many held-out documents in one device pass (each row = one theta)."""
+        m = self._model
+        docs = []
+        for inst in instances:
+            f = inst.getData().getFeatures()
+            docs.append(f[(f >= 0) & (f < m.numTypes)])   # unknown types are dropped, as in Mallet
+        lens = np.array([len(d) for d in docs], np.int64)
+        doc_ptr = np.zeros(len(docs) + 1, np.int64)
+        np.cumsum(lens, out=doc_ptr[1:])
+        tok = np.concatenate(docs).astype(np.int32) if len(docs) and doc_ptr[-1] > 0 else np.zeros(0, np.int32)
+        return m._samplers[0].infer(doc_ptr, tok, numIterations, thinning, burnIn, self.randomSeed)
+
+
+def _fmt(x: float) -> str:
+    return f"{x:.5f}"
+
+
+def _open_for_write(file):
+    if hasattr(file, "write"):
+        import contextlib
+        return contextlib.nullcontext(file)
+    return open(file, "w", encoding="utf-8")

