@@ -246,8 +246,10 @@ def test_c1_ll_per_token_within_one_percent_of_mallet_trajectory(oracle):
             ll = s.loglik() / len(tok)
             if mark >= 100:
                 rel = np.abs(ll - ref[:, i]) / np.abs(ref[:, i])
+                # within 1 % of a Mallet-faithful run from the same initial topics ...
                 assert rel.min() <= 0.01, (mode, mark, ll, ref[:, i].tolist())
-                assert abs(ll - ref[:, i].mean()) / abs(ref[:, i].mean()) <= 0.015, (mode, mark, ll)
+                # ... and inside the band the oracle's own seeds span (they differ by ~2 %), +-1 %
+                assert ref[:, i].min() * 1.01 <= ll <= ref[:, i].max() * 0.99, (mode, mark, ll, ref[:, i].tolist())
         s.close()
 
 
