@@ -97,9 +97,11 @@ typedef struct {
   double cum_tables_ms, cum_sample_ms, cum_finish_ms;
   int64_t cum_tokens_moved, cum_prior_bucket;
   int64_t cum_doc_topics;         /* sum over sampled tokens of the document's non-zero topics */
-  /* long-row document class (rows wider than slot_capacity): count, row slots, CTAs */
+  /* row-width classes: slot_capacity/ctas/smem above describe the narrowest class (the bulk);
+   * these the widest one (the longest documents): its document count, row slots, CTAs */
   int64_t long_docs;
   int32_t long_slot_capacity, long_ctas;
+  int32_t row_classes, reserved1;
 } b200lda_stats;
 
 /* Message of the calling thread's most recent failure ("" if none). Never NULL. */

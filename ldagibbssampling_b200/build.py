@@ -48,7 +48,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("B200LDA_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "b200lda.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -57,6 +58,7 @@ constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // d_counters: [0] scheduler (long class), [1..3] last sweep {moved, prior draws, nnz sum},
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
 constexpr int kCounters = 12;  // [9..11] sink for the stats of inference passes
+constexpr int kMaxClasses = 16;
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 constexpr int kPartial = 1184;   // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
 
@@ -102,11 +104,16 @@ struct DeviceCorpus {
   long long* d_word_ptr = nullptr;  // [V+1] word -> token CSR (training corpus only)
   int64_t* d_wtok = nullptr;        // [N]
   int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
-  int64_t n_long = 0;
   int max_doc_len = 0;
   std::vector<int64_t> h_doc_ptr, h_row_ptr;
   std::vector<int32_t> h_doc_order;
-  SweepShape shape_short, shape_long;
+  // Row-width classes, widest first: class i holds the documents whose packed row needs at most
+  // classes[i].shape.slot_cap slots; each class is one launch with shared memory sized to it.
+  struct DocClass {
+    int64_t begin = 0, end = 0;  // slice of doc_order
+    SweepShape shape;
+  };
+  std::vector<DocClass> classes;
 };
 
 }  // namespace
@@ -121,7 +128,7 @@ struct b200lda_ctx {
   int64_t launches = 0;
 
   DeviceCorpus corp;  // training documents
-  int small_row = 256;
+  int min_row = 64;  // narrowest row-width class
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
@@ -133,6 +140,10 @@ struct b200lda_ctx {
 
   // scratch
   unsigned long long* d_counters = nullptr;
+  unsigned long long* d_sched = nullptr;  // [kMaxClasses] document scheduler counter per class launch
+  // side streams so the row-width classes of one sweep run concurrently (fork/join by events)
+  cudaStream_t side[kMaxClasses] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxClasses] = {};
   int* d_bad = nullptr;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -267,12 +278,28 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
   return B200LDA_OK;
 }
 
-// Two document classes: rows of at most small_row slots (the bulk: small per-warp shared memory,
-// full occupancy) and the long tail (rows up to min(K, longest document)).
-int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp) {
-  const int longest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
-  TRY(shape_for(c, std::min(longest, c->small_row), 4, cp.max_doc_len, &cp.shape_short));
-  TRY(shape_for(c, longest, 1, cp.max_doc_len, &cp.shape_long));
+// Row-width classes with power-of-two slot capacities (min_row, 2 min_row, ... up to the widest
+// row): per-warp shared memory follows the row width, so the bulk of short documents leaves most
+// of the SM's 228 KB to the L1 cache and the long tail does not dictate everyone's occupancy.
+// len_ge[L] = number of documents with at least L tokens (documents are ordered longest first).
+int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>& len_ge) {
+  cp.classes.clear();
+  const int widest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
+  std::vector<int> caps;
+  for (int cap = c->min_row; cap < widest; cap *= 2) caps.push_back(cap);
+  caps.push_back(widest);
+  auto docs_with_row_above = [&](int cap) -> int64_t {  // rows are min(len, K) slots wide
+    if (cap >= c->K || cap + 1 >= (int)len_ge.size()) return 0;
+    return len_ge[(size_t)cap + 1];
+  };
+  for (int i = (int)caps.size() - 1; i >= 0; --i) {
+    DeviceCorpus::DocClass dc;
+    dc.begin = docs_with_row_above(caps[i]);
+    dc.end = i == 0 ? cp.D : docs_with_row_above(caps[i - 1]);
+    if (dc.end <= dc.begin) continue;
+    TRY(shape_for(c, caps[i], caps[i] > 256 ? 1 : 4, cp.max_doc_len, &dc.shape));
+    cp.classes.push_back(dc);
+  }
   return B200LDA_OK;
 }
 
@@ -314,22 +341,22 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
     max_len = std::max<int>(max_len, (int)len);
   }
   cp.h_row_ptr[num_docs] = off;
+  // visiting order: longest document first (counting sort); len_ge feeds the row-width classes
+  std::vector<int64_t> len_ge((size_t)max_len + 2, 0);
   {
-    const int small = std::min(std::max(32, round_up32(std::min(c->K, std::max(1, max_len)))), c->small_row);
     std::vector<int64_t> bucket((size_t)max_len + 2, 0);
-    int64_t n_long = 0;
     for (int64_t d = 0; d < num_docs; ++d) {
       const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
       bucket[(size_t)(max_len - len) + 1]++;  // descending length
-      if (std::min<int64_t>(len, c->K) > small) ++n_long;
+      len_ge[(size_t)len]++;
     }
+    for (int64_t L = max_len - 1; L >= 0; --L) len_ge[(size_t)L] += len_ge[(size_t)L + 1];
     for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
     cp.h_doc_order.resize((size_t)num_docs);
     for (int64_t d = 0; d < num_docs; ++d) {
       const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
       cp.h_doc_order[(size_t)bucket[(size_t)(max_len - len)]++] = (int32_t)d;
     }
-    cp.n_long = n_long;  // longest-first order puts exactly the long class in front
   }
   if (num_docs > cp.cap_docs) {
     dev_free(cp.d_doc_ptr);
@@ -388,7 +415,8 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
     c->launches += 1;
   }
   CU(cudaGetLastError());
-  TRY(configure_sweep(c, cp));
+  cp.D = num_docs;
+  TRY(configure_sweep(c, cp, len_ge));
   CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
 }
@@ -464,7 +492,7 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
 
 template <int MODE, bool LIVE>
 int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
-                 unsigned long long* counter) {
+                 unsigned long long* counter, cudaStream_t stream) {
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
@@ -475,21 +503,34 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   const int ctas = (int)std::max<int64_t>(
       1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
   if (sh.tables_in_smem)
-    k_gibbs_sweep<MODE, LIVE, true><<<ctas, sh.warps_per_cta * 32, sh.smem, c->stream>>>(p);
+    k_gibbs_sweep<MODE, LIVE, true><<<ctas, sh.warps_per_cta * 32, sh.smem, stream>>>(p);
   else
-    k_gibbs_sweep<MODE, LIVE, false><<<ctas, sh.warps_per_cta * 32, sh.smem, c->stream>>>(p);
+    k_gibbs_sweep<MODE, LIVE, false><<<ctas, sh.warps_per_cta * 32, sh.smem, stream>>>(p);
   c->launches += 1;
   CU(cudaGetLastError());
   return B200LDA_OK;
 }
 
-// One pass over a corpus = the long-row class first (few, long-running warps), then the bulk.
+// One pass over a corpus = one launch per row-width class, all in flight together: the wide
+// classes (few, long documents: each a long serial chain on one warp) go to side streams forked
+// off the context's stream, the bulk runs on the context's stream, and the sweep joins them. A
+// long document's latency is then hidden behind the bulk instead of being a launch of its own.
 template <int MODE, bool LIVE>
 int launch_sweep(b200lda_ctx* c, const DeviceCorpus& cp, const SweepParams& p) {
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
-  CU(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->stream));
-  TRY((launch_class<MODE, LIVE>(c, p, cp.shape_long, 0, cp.n_long, c->d_counters + 0)));
-  TRY((launch_class<MODE, LIVE>(c, p, cp.shape_short, cp.n_long, cp.D, c->d_counters + 8)));
+  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
+  const size_t n = cp.classes.size();
+  if (n == 0) return B200LDA_OK;
+  if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
+  for (size_t i = 0; i + 1 < n; ++i) {
+    CU(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    TRY((launch_class<MODE, LIVE>(c, p, cp.classes[i].shape, cp.classes[i].begin, cp.classes[i].end, c->d_sched + i,
+                                  c->side[i])));
+    CU(cudaEventRecord(c->ev_join[i], c->side[i]));
+  }
+  TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
+                                c->d_sched + (n - 1), c->stream)));
+  for (size_t i = 0; i + 1 < n; ++i) CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   return B200LDA_OK;
 }
 
@@ -591,12 +632,9 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->beta = cfg->beta;
   c->sm_count = prop.multiProcessorCount;
   c->layout = make_layout(c->K);
-  {
-    // Short-row class: the widest row that still lets 4 CTAs of 8 warps share an SM's shared
-    // memory (the kernel's registers allow no more than 4 anyway), so it never costs occupancy.
-    const int64_t tab = 2 * (int64_t)sizeof(float) * c->K;
-    const int64_t cap4 = (((int64_t)kMaxSmemPerCta / 4 - 1024 - tab) / 64) & ~(int64_t)31;
-    c->small_row = (int)std::max<int64_t>(256, std::min<int64_t>(cap4, 65536));
+  if (const char* e = std::getenv("B200LDA_MIN_ROW")) {  // tuning knob for experiments
+    const int v = atoi(e);
+    if (v >= 32) c->min_row = round_up32(v);
   }
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
@@ -612,6 +650,15 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
     c->own_stream = true;
   }
   c->ev_pool.reserve(4 * kEventPool);
+  {
+    int lo = 0, hi = 0;  // wide-row classes get the higher priority: their chains are the critical path
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kMaxClasses && ok; ++i)
+      ok = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return bail(fail(B200LDA_ECUDA, "creating side streams failed"));
+  }
   const size_t VK = (size_t)c->V * c->K;
   const bool multi = cfg->world_size > 1;
   if ((rc = dev_alloc_t(c, &c->d_nwk, VK)) || (rc = dev_alloc_t(c, &c->d_nk, c->K)) ||
@@ -619,7 +666,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
@@ -654,12 +701,18 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_alpha);
   dev_free(c->d_lg_alpha);
   dev_free(c->d_counters);
+  dev_free(c->d_sched);
   dev_free(c->d_bad);
   dev_free(c->d_partial);
   dev_free(c->d_hist_scratch);
   if (c->d_stage) cudaFree(c->d_stage);
   for (auto& e : c->ev_pool)
     if (e) cudaEventDestroy(e);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < kMaxClasses; ++i) {
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+  }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
   delete c;
@@ -1087,13 +1140,18 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->kernel_launches = c->launches;
   out->tokens_sampled = c->tokens_sampled;
   out->device_bytes = c->device_bytes;
-  out->smem_bytes_per_cta = (int32_t)c->corp.shape_short.smem;
-  out->warps_per_cta = c->corp.shape_short.warps_per_cta;
-  out->ctas = c->corp.shape_short.ctas;
-  out->slot_capacity = c->corp.shape_short.slot_cap;
-  out->long_docs = c->corp.n_long;
-  out->long_slot_capacity = c->corp.shape_long.slot_cap;
-  out->long_ctas = c->corp.shape_long.ctas;
+  if (!c->corp.classes.empty()) {
+    const SweepShape& bulk = c->corp.classes.back().shape;    // narrowest rows
+    const SweepShape& tail = c->corp.classes.front().shape;   // widest rows
+    out->smem_bytes_per_cta = (int32_t)bulk.smem;
+    out->warps_per_cta = bulk.warps_per_cta;
+    out->ctas = bulk.ctas;
+    out->slot_capacity = bulk.slot_cap;
+    out->long_docs = c->corp.classes.size() > 1 ? c->corp.classes.front().end - c->corp.classes.front().begin : 0;
+    out->long_slot_capacity = tail.slot_cap;
+    out->long_ctas = tail.ctas;
+    out->row_classes = (int32_t)c->corp.classes.size();
+  }
   if (c->in_sweep) return B200LDA_OK;  // timings of an open sweep are not resolvable yet
   TRY(resolve_events(c));
   out->last_tables_ms = c->last_tables_ms;

@@ -84,8 +84,12 @@ __device__ __forceinline__ void row_shift_down(uint32_t* slots, int a, int b, in
   }
 }
 
+#ifndef B200LDA_SWEEP_MIN_CTAS
+#define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
+#endif
+
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(256) k_gibbs_sweep(const SweepParams p) {
+__global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
