@@ -117,7 +117,8 @@ void b200lda_destroy(b200lda_ctx* ctx);
 
 /* model.addInstances(InstanceList) — corpus half           cmu_ron/TrainAndPredict.java:162,
  * Flattened FeatureSequences: doc d = tok_word[doc_ptr[d] .. doc_ptr[d+1]).   cmu/…:260
- * Copies to the device and packs the doc->token and word->token CSR orders. Replaces any
+ * Copies to the device and packs the doc->token CSR order (row offsets, longest-first visiting
+ * order and CSR/word-id validation are computed on the device). Replaces any
  * corpus already loaded (updateModel: pass old + new documents, cmu_ron/…:173-177). */
 int b200lda_load_corpus(b200lda_ctx* ctx, int64_t num_docs, const int64_t* doc_ptr,
                         const int32_t* tok_word);
@@ -180,6 +181,11 @@ int b200lda_get_nk(b200lda_ctx* ctx, int32_t* nk /* K */);
 /* Sparse doc-topic rows, topics ascending: row d = [row_ptr[d], row_ptr[d]+nnz). Pass topic ==
  * NULL to only size: row_ptr (num_docs+1 entries) is filled either way. */
 int b200lda_get_ndk_csr(b200lda_ctx* ctx, int64_t* row_ptr, int32_t* topic, int32_t* count);
+/* The word -> token CSR order of the loaded corpus (built on the device on first request; the
+ * sampler itself counts n_wk straight from the doc order): word w's tokens are
+ * word_tokens[word_ptr[w] .. word_ptr[w+1]) as indices into tok_word; order inside a word is
+ * unspecified. word_ptr has V+1 entries; word_tokens (num_tokens entries) may be NULL. */
+int b200lda_get_word_order(b200lda_ctx* ctx, int64_t* word_ptr, int64_t* word_tokens);
 /* model.getTopicProbabilities(topicSequence)               cmu_ron/TrainAndPredict.java:143,
  * theta for documents [doc_begin, doc_end): (doc_end-doc_begin)*K doubles.    cmu/…:113 */
 int b200lda_get_theta(b200lda_ctx* ctx, int64_t doc_begin, int64_t doc_end, double* theta);

@@ -85,6 +85,7 @@ SYMBOLS = [
     ("b200lda_get_nwk", C.c_int, [_P, _P]),
     ("b200lda_get_nk", C.c_int, [_P, _P]),
     ("b200lda_get_ndk_csr", C.c_int, [_P, _P, _P, _P]),
+    ("b200lda_get_word_order", C.c_int, [_P, _P, _P]),
     ("b200lda_get_theta", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("b200lda_get_phi", C.c_int, [_P, _P]),
     ("b200lda_set_alpha", C.c_int, [_P, _P]),
@@ -267,6 +268,13 @@ class Sampler:
         count = np.zeros(max(n, 1), np.int32)
         self._check(self._lib.b200lda_get_ndk_csr(self._h, _ptr(row_ptr), _ptr(topic), _ptr(count)))
         return row_ptr, topic[:n], count[:n]
+
+    def word_order(self):
+        """(word_ptr int64[V+1], word_tokens int64[N]): the word -> token CSR order."""
+        word_ptr = np.zeros(self.V + 1, np.int64)
+        toks = np.zeros(max(self.num_tokens, 1), np.int64)
+        self._check(self._lib.b200lda_get_word_order(self._h, _ptr(word_ptr), _ptr(toks)))
+        return word_ptr, toks[:self.num_tokens]
 
     def theta(self, doc_begin=0, doc_end=None):
         doc_end = self.num_docs if doc_end is None else doc_end

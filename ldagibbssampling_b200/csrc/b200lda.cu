@@ -103,10 +103,9 @@ struct DeviceCorpus {
   int32_t* d_doc_order = nullptr; // [D]   long-row class first, longest first
   long long* d_word_ptr = nullptr;  // [V+1] word -> token CSR (training corpus only)
   int64_t* d_wtok = nullptr;        // [N]
-  int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0;
+  int64_t cap_docs = 0, cap_tokens = 0, cap_rows = 0, rows_total = 0;
   int max_doc_len = 0;
-  std::vector<int64_t> h_doc_ptr, h_row_ptr;
-  std::vector<int32_t> h_doc_order;
+  bool word_order_built = false;
   // Row-width classes, widest first: class i holds the documents whose packed row needs at most
   // classes[i].shape.slot_cap slots; each class is one launch with shared memory sized to it.
   struct DocClass {
@@ -318,46 +317,17 @@ void free_corpus(DeviceCorpus& cp) {
   cp.cap_docs = cp.cap_tokens = cp.cap_rows = 0;
 }
 
-// Validates the CSR, plans the packed n_dk rows (capacity min(K, L_d)) and the visiting order
-// (long-row class first, each class longest document first — a counting sort), uploads
-// everything. `with_word_order` adds the word -> token CSR (device counting sort; its histogram
-// pass also validates the word ids).
-int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word,
-                bool with_word_order) {
+// Uploads a CSR document set and plans it ON THE DEVICE: CSR validation, document-length
+// histogram, packed n_dk row offsets (capacity min(K, L_d), two-level scan), visiting order
+// (longest first, counting sort) and word-id validation. Only the 64 K-bin length histogram comes
+// back to the host, which derives the row-width classes from it.
+int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_t* doc_ptr, const int32_t* tok_word) {
   if (num_docs < 0 || !doc_ptr) return fail(B200LDA_EINVAL, "bad corpus arguments");
   if (doc_ptr[0] != 0) return fail(B200LDA_EINVAL, "doc_ptr[0] must be 0");
   const int64_t N = doc_ptr[num_docs];
+  if (N < 0) return fail(B200LDA_EINVAL, "doc_ptr[num_docs] is negative");
   if (N > 0 && !tok_word) return fail(B200LDA_EINVAL, "tok_word is null");
-  cp.h_doc_ptr.assign(doc_ptr, doc_ptr + num_docs + 1);
-  cp.h_row_ptr.resize(num_docs + 1);
-  int max_len = 0;
-  int64_t off = 0;
-  for (int64_t d = 0; d < num_docs; ++d) {
-    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-    if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", (long long)d);
-    if (len > 65535) return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", (long long)d, (long long)len);
-    cp.h_row_ptr[d] = off;
-    off += std::min<int64_t>(len, c->K);
-    max_len = std::max<int>(max_len, (int)len);
-  }
-  cp.h_row_ptr[num_docs] = off;
-  // visiting order: longest document first (counting sort); len_ge feeds the row-width classes
-  std::vector<int64_t> len_ge((size_t)max_len + 2, 0);
-  {
-    std::vector<int64_t> bucket((size_t)max_len + 2, 0);
-    for (int64_t d = 0; d < num_docs; ++d) {
-      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-      bucket[(size_t)(max_len - len) + 1]++;  // descending length
-      len_ge[(size_t)len]++;
-    }
-    for (int64_t L = max_len - 1; L >= 0; --L) len_ge[(size_t)L] += len_ge[(size_t)L + 1];
-    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
-    cp.h_doc_order.resize((size_t)num_docs);
-    for (int64_t d = 0; d < num_docs; ++d) {
-      const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
-      cp.h_doc_order[(size_t)bucket[(size_t)(max_len - len)]++] = (int32_t)d;
-    }
-  }
+  cp.word_order_built = false;
   if (num_docs > cp.cap_docs) {
     dev_free(cp.d_doc_ptr);
     dev_free(cp.d_row_ptr);
@@ -375,49 +345,105 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
     dev_free(cp.d_wtok);
     TRY(dev_alloc_t(c, &cp.d_tok_word, (size_t)N));
     TRY(dev_alloc_t(c, &cp.d_z, (size_t)N));
-    if (with_word_order) TRY(dev_alloc_t(c, &cp.d_wtok, (size_t)N));
     cp.cap_tokens = N;
-  }
-  if (off > cp.cap_rows) {
-    dev_free(cp.d_rows);
-    TRY(dev_alloc_t(c, &cp.d_rows, (size_t)off));
-    cp.cap_rows = off;
   }
   cp.D = num_docs;
   cp.N = N;
-  cp.max_doc_len = max_len;
   CU(cudaMemcpyAsync(cp.d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(cp.d_row_ptr, cp.h_row_ptr.data(), sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
-  if (num_docs > 0)
-    CU(cudaMemcpyAsync(cp.d_doc_order, cp.h_doc_order.data(), sizeof(int32_t) * num_docs, cudaMemcpyHostToDevice, c->stream));
   if (N > 0) CU(cudaMemcpyAsync(cp.d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
 
+  // scratch: [len_hist 65537 | cursor 65537 | len_start 65537 | bad_doc | block sums/offsets ...]
+  constexpr int kBins = 65537;
+  const int64_t nblocks = (num_docs + kScanBlock - 1) / kScanBlock;
+  const size_t words64 = 3 * (size_t)kBins + 1 + 2 * (size_t)(nblocks + 1);
+  TRY(ensure_stage(c, sizeof(unsigned long long) * words64));
+  unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(c->d_stage);
+  unsigned long long* d_cursor = d_hist + kBins;
+  long long* d_len_start = reinterpret_cast<long long*>(d_cursor + kBins);
+  long long* d_bad_doc = d_len_start + kBins;
+  unsigned long long* d_block_sum = reinterpret_cast<unsigned long long*>(d_bad_doc + 1);
+  long long* d_block_off = reinterpret_cast<long long*>(d_block_sum + nblocks + 1);
+  CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 2 * kBins, c->stream));
+  const long long no_bad = 0x7fffffffffffffffLL;
+  CU(cudaMemcpyAsync(d_bad_doc, &no_bad, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  std::vector<unsigned long long> h_hist((size_t)kBins, 0);
+  long long bad_doc = no_bad;
+  int bad_word = 0;
+  if (num_docs > 0) {
+    k_doc_lengths<<<grid_for(c, num_docs, 256), 256, 0, c->stream>>>(num_docs, cp.d_doc_ptr, d_hist, d_bad_doc);
+    k_row_block_sums<<<(unsigned)nblocks, kScanBlock, 0, c->stream>>>(num_docs, c->K, cp.d_doc_ptr, d_block_sum);
+    k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>((int)nblocks, d_block_sum, d_block_off);
+    k_row_ptr_apply<<<(unsigned)nblocks, kScanBlock, 0, c->stream>>>(num_docs, c->K, cp.d_doc_ptr, d_block_off, cp.d_row_ptr);
+    c->launches += 4;
+  } else {
+    CU(cudaMemsetAsync(cp.d_row_ptr, 0, sizeof(int64_t), c->stream));
+  }
+  if (N > 0) {
+    k_validate_words<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, cp.d_tok_word, c->d_bad);
+    c->launches += 1;
+  }
+  CU(cudaMemcpyAsync(h_hist.data(), d_hist, sizeof(unsigned long long) * kBins, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&bad_doc, d_bad_doc, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&bad_word, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  if (bad_doc != no_bad) {
+    const int64_t len = doc_ptr[bad_doc + 1] - doc_ptr[bad_doc];
+    if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", bad_doc);
+    return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", bad_doc, (long long)len);
+  }
+  if (bad_word) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
+
+  // host: 64 K bins -> longest document, row capacity, len_ge, class boundaries, order offsets
+  int max_len = 0;
+  int64_t rows_total = 0;
+  for (int L = 0; L < kBins; ++L)
+    if (h_hist[(size_t)L]) {
+      max_len = L;
+      rows_total += (int64_t)h_hist[(size_t)L] * std::min(L, c->K);
+    }
+  cp.max_doc_len = max_len;
+  cp.rows_total = rows_total;
+  std::vector<int64_t> len_ge((size_t)max_len + 2, 0);
+  for (int L = max_len; L >= 0; --L) len_ge[(size_t)L] = len_ge[(size_t)L + 1] + (int64_t)h_hist[(size_t)L];
+  std::vector<long long> len_start((size_t)kBins, 0);  // documents longer than L come first
+  for (int L = 0; L <= max_len; ++L) len_start[(size_t)L] = len_ge[(size_t)L + 1];
+  if (rows_total > cp.cap_rows) {
+    dev_free(cp.d_rows);
+    TRY(dev_alloc_t(c, &cp.d_rows, (size_t)rows_total));
+    cp.cap_rows = rows_total;
+  }
+  if (num_docs > 0) {
+    CU(cudaMemcpyAsync(d_len_start, len_start.data(), sizeof(long long) * kBins, cudaMemcpyHostToDevice, c->stream));
+    k_doc_order_scatter<<<grid_for(c, num_docs, 256), 256, 0, c->stream>>>(num_docs, cp.d_doc_ptr, d_len_start, d_cursor,
+                                                                         cp.d_doc_order);
+    c->launches += 1;
+  }
+  CU(cudaGetLastError());
+  TRY(configure_sweep(c, cp, len_ge));
+  CU(cudaStreamSynchronize(c->stream));  // len_start (host vector) must outlive the copy
+  return B200LDA_OK;
+}
+
+// word -> token CSR of a packed corpus (device counting sort), built on demand: the sampler itself
+// never needs it (n_wk is counted straight from the doc order), b200lda_get_word_order does.
+int build_word_order(b200lda_ctx* c, DeviceCorpus& cp) {
+  if (cp.word_order_built) return B200LDA_OK;
+  if (!cp.d_word_ptr) TRY(dev_alloc_t(c, &cp.d_word_ptr, (size_t)c->V + 1));
+  if (!cp.d_wtok && cp.N > 0) TRY(dev_alloc_t(c, &cp.d_wtok, (size_t)cp.cap_tokens));
   TRY(ensure_stage(c, sizeof(unsigned long long) * (size_t)c->V));
   unsigned long long* d_wcount = reinterpret_cast<unsigned long long*>(c->d_stage);
   CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
   CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
-  if (N > 0) {
-    k_word_hist<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, cp.d_tok_word, d_wcount, c->d_bad);
-    c->launches += 1;
-  }
-  if (with_word_order) {
-    if (!cp.d_word_ptr) TRY(dev_alloc_t(c, &cp.d_word_ptr, (size_t)c->V + 1));
-    k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>(c->V, d_wcount, cp.d_word_ptr);
-    c->launches += 1;
-  }
-  int bad = 0;
-  CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (bad) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
-  if (with_word_order && N > 0) {
-    CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
-    k_word_scatter<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, cp.d_tok_word, cp.d_word_ptr, d_wcount, cp.d_wtok);
-    c->launches += 1;
-  }
+  if (cp.N > 0) k_word_hist<<<grid_for(c, cp.N, 256), 256, 0, c->stream>>>(cp.N, c->V, cp.d_tok_word, d_wcount, c->d_bad);
+  k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>(c->V, d_wcount, cp.d_word_ptr);
+  CU(cudaMemsetAsync(d_wcount, 0, sizeof(unsigned long long) * c->V, c->stream));
+  if (cp.N > 0) k_word_scatter<<<grid_for(c, cp.N, 256), 256, 0, c->stream>>>(cp.N, cp.d_tok_word, cp.d_word_ptr, d_wcount, cp.d_wtok);
+  c->launches += 3;
   CU(cudaGetLastError());
-  cp.D = num_docs;
-  TRY(configure_sweep(c, cp, len_ge));
   CU(cudaStreamSynchronize(c->stream));
+  cp.word_order_built = true;
   return B200LDA_OK;
 }
 
@@ -723,7 +749,7 @@ int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr
   if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
   c->corpus_loaded = false;
   c->assigned = false;
-  TRY(pack_corpus(c, c->corp, num_docs, doc_ptr, tok_word, true));
+  TRY(pack_corpus(c, c->corp, num_docs, doc_ptr, tok_word));
   c->corpus_loaded = true;
   return B200LDA_OK;
 }
@@ -751,13 +777,13 @@ int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
     }
     c->launches += 1;
   }
-  // n_wk from the word -> token order, n_k as its column sums
+  // n_wk by integer atomics straight from the doc -> token order, n_k as its column sums
   const size_t VK = (size_t)c->V * c->K;
   CU(cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream));
   CU(cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream));
   CU(cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream));
   if (N > 0) {
-    k_count_sorted<<<grid_for(c, N, 256, 16), 256, 0, c->stream>>>(N, c->K, cp.d_wtok, cp.d_tok_word, cp.d_z, c->d_nwk);
+    k_count_direct<<<grid_for(c, N, 256, 16), 256, 0, c->stream>>>(N, c->K, cp.d_tok_word, cp.d_z, c->d_nwk);
     const int rows_per_block = 256;
     dim3 grid((c->K + 255) / 256, (c->V + rows_per_block - 1) / rows_per_block);
     k_col_sums<<<grid, 256, 0, c->stream>>>(c->V, c->K, rows_per_block, c->d_nwk, c->d_nk);
@@ -910,7 +936,7 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
   // held-out documents are packed like a corpus of their own; the trained counts stay frozen
   DeviceCorpus cp;
   const int64_t bytes_before = c->device_bytes;
-  int rc = pack_corpus(c, cp, num_docs, doc_ptr, tok_word, false);
+  int rc = pack_corpus(c, cp, num_docs, doc_ptr, tok_word);
   int32_t* d_acc = nullptr;
   double* d_theta = nullptr;
   auto cleanup = [&](int code) {
@@ -1041,17 +1067,34 @@ int b200lda_get_ndk_csr(b200lda_ctx* c, int64_t* row_ptr, int32_t* topic, int32_
   row_ptr[0] = 0;
   for (int64_t d = 0; d < cp.D; ++d) row_ptr[d + 1] = row_ptr[d] + nnz[d];
   if (!topic || !count) return B200LDA_OK;
-  const int64_t cap = cp.h_row_ptr[cp.D];
+  std::vector<int64_t> h_row_ptr((size_t)cp.D + 1, 0);
+  CU(cudaMemcpyAsync(h_row_ptr.data(), cp.d_row_ptr, sizeof(int64_t) * (cp.D + 1), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int64_t cap = h_row_ptr[cp.D];
   std::vector<uint32_t> rows((size_t)cap);
   if (cap > 0) CU(cudaMemcpyAsync(rows.data(), cp.d_rows, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int64_t d = 0; d < cp.D; ++d) {
-    const uint32_t* src = rows.data() + cp.h_row_ptr[d];
+    const uint32_t* src = rows.data() + h_row_ptr[d];
     for (int32_t j = 0; j < nnz[d]; ++j) {
       topic[row_ptr[d] + j] = (int32_t)(src[j] >> 16);
       count[row_ptr[d] + j] = (int32_t)(src[j] & 0xffffu);
     }
   }
+  return B200LDA_OK;
+}
+
+int b200lda_get_word_order(b200lda_ctx* c, int64_t* word_ptr, int64_t* word_tokens) {
+  TRY(enter(c));
+  if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
+  if (!word_ptr) return fail(B200LDA_EINVAL, "word_ptr is null");
+  DeviceCorpus& cp = c->corp;
+  TRY(build_word_order(c, cp));
+  static_assert(sizeof(long long) == sizeof(int64_t), "word_ptr layout");
+  CU(cudaMemcpyAsync(word_ptr, cp.d_word_ptr, sizeof(int64_t) * ((size_t)c->V + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (word_tokens && cp.N > 0)
+    CU(cudaMemcpyAsync(word_tokens, cp.d_wtok, sizeof(int64_t) * cp.N, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
 }
 

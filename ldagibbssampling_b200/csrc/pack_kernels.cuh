@@ -40,6 +40,98 @@ __global__ void k_widen_z(int64_t N, const uint16_t* __restrict__ in, int32_t* _
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) out[i] = (int32_t)in[i];
 }
 
+// Streaming validation of word ids (no atomics): flags any id outside [0, V).
+__global__ void k_validate_words(int64_t N, int V, const int32_t* __restrict__ tok_word, int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool any = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int32_t w = tok_word[i];
+    any |= (w < 0) | (w >= V);
+  }
+  if (any) *bad = 1;
+}
+
+// Document plan, pass 1: validates the CSR (monotone, length <= 65535; *bad = 1 + first bad doc)
+// and histograms document lengths (65536 + 1 bins).
+__global__ void k_doc_lengths(int64_t D, const int64_t* __restrict__ doc_ptr, unsigned long long* __restrict__ len_hist,
+                              long long* __restrict__ bad_doc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += stride) {
+    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    if (len < 0 || len > 65535) {
+      atomicMin(bad_doc, (long long)d);
+    } else {
+      atomicAdd(len_hist + len, 1ull);
+    }
+  }
+}
+
+// Document plan, pass 2 (two-level exclusive scan of row capacities min(len, K) -> row_ptr):
+// block sums, then (after a single-block scan of the sums) per-block rescan + offset.
+constexpr int kScanBlock = 1024;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* s_warp, long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long y = __shfl_up_sync(kFullMask, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long t = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(kFullMask, t, d);
+      if (lane >= d) t += y;
+    }
+    s_warp[lane] = t;
+  }
+  __syncthreads();
+  const long long off = warp ? s_warp[warp - 1] : 0;
+  *total = s_warp[(blockDim.x >> 5) - 1];
+  return off + x - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_row_block_sums(int64_t D, int K, const int64_t* __restrict__ doc_ptr, unsigned long long* __restrict__ block_sum) {
+  __shared__ long long s_warp[32];
+  const int64_t d = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  long long v = 0;
+  if (d < D) v = min((long long)(doc_ptr[d + 1] - doc_ptr[d]), (long long)K);
+  long long total;
+  block_exclusive_scan(v, s_warp, &total);
+  if (threadIdx.x == 0) block_sum[blockIdx.x] = (unsigned long long)total;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+k_row_ptr_apply(int64_t D, int K, const int64_t* __restrict__ doc_ptr, const long long* __restrict__ block_off,
+                int64_t* __restrict__ row_ptr) {
+  __shared__ long long s_warp[32];
+  const int64_t d = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  long long v = 0;
+  if (d < D) v = min((long long)(doc_ptr[d + 1] - doc_ptr[d]), (long long)K);
+  long long total;
+  const long long ex = block_exclusive_scan(v, s_warp, &total);
+  const long long base = block_off[blockIdx.x];
+  if (d < D) row_ptr[d] = base + ex;
+  if (d == D - 1) row_ptr[D] = base + ex + v;
+}
+
+// Document plan, pass 3: visiting order = longest document first. len_start[L] = number of
+// documents longer than L (from the length histogram); ties are ordered by arrival.
+__global__ void k_doc_order_scatter(int64_t D, const int64_t* __restrict__ doc_ptr, const long long* __restrict__ len_start,
+                                    unsigned long long* __restrict__ cursor, int32_t* __restrict__ doc_order) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += stride) {
+    const int64_t len = doc_ptr[d + 1] - doc_ptr[d];
+    const unsigned long long r = atomicAdd(cursor + len, 1ull);
+    doc_order[len_start[len] + (long long)r] = (int32_t)d;
+  }
+}
+
 // Validates word ids and histograms them (word -> token CSR, pass 1).
 __global__ void k_word_hist(int64_t N, int V, const int32_t* __restrict__ tok_word,
                             unsigned long long* __restrict__ word_count, int* __restrict__ bad) {
@@ -115,6 +207,15 @@ k_count_sorted(int64_t N, int K, const int64_t* __restrict__ wtok, const int32_t
     const int64_t t = wtok[i];
     atomicAdd(nwk + (size_t)tok_word[t] * K + z[t], 1);
   }
+}
+
+// n_wk straight from the doc -> token order (no word order needed): streaming reads, random REDs.
+__global__ void __launch_bounds__(256)
+k_count_direct(int64_t N, int K, const int32_t* __restrict__ tok_word, const uint16_t* __restrict__ z,
+               int32_t* __restrict__ nwk) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+    atomicAdd(nwk + (size_t)tok_word[i] * K + z[i], 1);
 }
 
 // n_k = column sums of n_wk: each block reduces a slab of rows, one thread per topic column.

@@ -164,3 +164,32 @@ def test_errors_are_reported_not_swallowed(oracle):
     assert e.value.code == -6  # ERANGE: topic >= K
     with pytest.raises(L.B200LDAError):
         L.Sampler(0, 10, 1.0, 0.1)
+
+
+def test_word_order_csr_is_a_permutation_grouped_by_word(oracle):
+    D, V, K = 700, 300, 8
+    dp, tok = oracle.gen_corpus(D, V, 30.0, 6, 16)
+    s = _sampler(K, V, seed=1)
+    s.load_corpus(dp, tok)
+    word_ptr, toks = s.word_order()
+    assert word_ptr[0] == 0 and word_ptr[-1] == len(tok)
+    assert np.array_equal(np.diff(word_ptr), np.bincount(tok, minlength=V))
+    assert np.array_equal(np.sort(toks), np.arange(len(tok)))          # a bijection on token indices
+    assert np.array_equal(tok[toks], np.repeat(np.arange(V), np.diff(word_ptr)))  # grouped by word
+
+
+def test_corpus_validation_on_device(oracle):
+    import ldagibbssampling_b200 as L
+    s = _sampler(8, 10, seed=1)
+    with pytest.raises(L.B200LDAError) as e:   # non-monotone CSR
+        s._check(s._lib.b200lda_load_corpus(s._h, 2, np.array([0, 3, 2], np.int64).ctypes.data,
+                                            np.array([1, 2, 3], np.int32).ctypes.data))
+    assert e.value.code == -1
+    long_doc = np.zeros(70000, np.int32)
+    with pytest.raises(L.B200LDAError) as e:   # document longer than 65535 tokens
+        s.load_corpus(np.array([0, 70000], np.int64), long_doc)
+    assert e.value.code == -6
+    s.load_corpus(np.array([0, 65535], np.int64), long_doc[:65535])   # the limit itself is fine
+    s.init_assignments(None)
+    s.sweep(1)
+    assert s.nk().sum() == 65535
