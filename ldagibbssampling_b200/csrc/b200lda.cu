@@ -244,7 +244,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
   sh.slot_cap = slot_cap;
   sh.doc_chunk = doc_chunk;
   const size_t tab = 2 * sizeof(float) * (size_t)c->K;
-  const size_t per_warp = 8 * (size_t)slot_cap;
+  const size_t per_warp = (size_t)kSmemBytesPerSlot * (size_t)slot_cap;
   bool ok = false;
   for (int ts = 1; ts >= 0 && !ok; --ts) {
     for (int wpc = 8; wpc >= 1 && !ok; wpc >>= 1) {

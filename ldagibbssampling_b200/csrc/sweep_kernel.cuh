@@ -59,7 +59,13 @@ struct SweepParams {
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
 };
 
-constexpr int kGroup = 4;  // tiles whose gathers are in flight together
+#ifndef B200LDA_SWEEP_GROUP
+#define B200LDA_SWEEP_GROUP 4  // measured on B200: 4 > 3 > 2 > 1 (profiles/r01_tuning.md)
+#endif
+constexpr int kGroup = B200LDA_SWEEP_GROUP;  // tiles whose gathers are in flight together
+
+// Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot.
+constexpr int kSmemBytesPerSlot = 8;
 
 // Rows [a, b) move one slot up (to [a+1, b+1)); chunks from the top so nothing is overwritten.
 __device__ __forceinline__ void row_shift_up(uint32_t* slots, int a, int b, int lane) {
