@@ -193,10 +193,29 @@ int b200lda_get_theta(b200lda_ctx* ctx, int64_t doc_begin, int64_t doc_end, doub
  * cmu_ron/TrainAndPredict.java:231). */
 int b200lda_get_phi(b200lda_ctx* ctx, double* phi);
 
-/* Hyper-parameters (host-side optimisation hooks; setOptimizeInterval(20) cmu_ron/…:163). */
+/* Hyper-parameters. */
 int b200lda_set_alpha(b200lda_ctx* ctx, const double* alpha /* K */);
 int b200lda_get_alpha(b200lda_ctx* ctx, double* alpha /* K */);
 int b200lda_set_beta(b200lda_ctx* ctx, double beta);
+int b200lda_get_beta(b200lda_ctx* ctx, double* beta);
+
+/* Hyper-parameter optimisation: model.setOptimizeInterval(20)   cmu_ron/TrainAndPredict.java:163,
+ * (ParallelTopicModel.optimizeAlpha / optimizeBeta inside estimate()).          cmu/…:261
+ *   hyper_begin(width)  allocate + clear the histograms; width > longest document over ALL shards
+ *   hyper_collect       add the current n_dk rows: docLengthCounts[n], topicDocCounts[k][n]
+ *                       (Mallet's workers do this on iterations % saveSampleInterval == 0)
+ *   hyper_buffer        device address + int32 count ((K+1)*width) to sum over shards first
+ *   hyper_get           host copies of the histograms (either pointer may be NULL)
+ *   optimize_alpha      Dirichlet.learnParameters(alpha, topicDocCounts, docLengthCounts)
+ *                       (Gamma(1.00001, 1) prior, 200 rounds); installs alpha, clears histograms
+ *   optimize_beta       Dirichlet.learnSymmetricConcentration over n_wk cell values and n_k;
+ *                       installs beta = betaSum / V. */
+int b200lda_hyper_begin(b200lda_ctx* ctx, int32_t width);
+int b200lda_hyper_collect(b200lda_ctx* ctx);
+int b200lda_hyper_buffer(b200lda_ctx* ctx, void** d_buf, int64_t* count);
+int b200lda_hyper_get(b200lda_ctx* ctx, int32_t* topic_doc_counts /* K*width */, int32_t* doc_length_counts /* width */);
+int b200lda_optimize_alpha(b200lda_ctx* ctx);
+int b200lda_optimize_beta(b200lda_ctx* ctx);
 
 /* Checkpoint/resume hooks (replaces Java serialisation, cmu_ron/TrainAndPredict.java:179-200):
  * sweep counter continues the Philox stream of a restored chain. */

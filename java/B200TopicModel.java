@@ -70,6 +70,12 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   private static final MethodHandle SET_ALPHA = fn("b200lda_set_alpha", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   private static final MethodHandle INFER = fn("b200lda_infer", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG,
       ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS));
+  private static final MethodHandle HYPER_BEGIN = fn("b200lda_hyper_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+  private static final MethodHandle HYPER_COLLECT = fn("b200lda_hyper_collect", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+  private static final MethodHandle OPTIMIZE_ALPHA = fn("b200lda_optimize_alpha", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+  private static final MethodHandle OPTIMIZE_BETA = fn("b200lda_optimize_beta", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+  private static final MethodHandle GET_ALPHA = fn("b200lda_get_alpha", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+  private static final MethodHandle GET_BETA = fn("b200lda_get_beta", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   private static final MethodHandle SET_SWEEP_COUNTER =
       fn("b200lda_set_sweep_counter", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
 
@@ -98,7 +104,7 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   public LabelAlphabet topicAlphabet;
   public int numTypes;
   public int numIterations = 1000, burninPeriod = 200, optimizeInterval = 50, showTopicsInterval = 50,
-      wordsPerTopic = 7, numThreads = 1, randomSeed = -1;
+      wordsPerTopic = 7, numThreads = 1, randomSeed = -1, saveSampleInterval = 10;
 
   private transient MemorySegment ctx = MemorySegment.NULL;
   private transient Arena arena;
@@ -122,7 +128,7 @@ public class B200TopicModel implements Serializable, AutoCloseable {
 
   public void setNumIterations(int n) { numIterations = n; }
   public void setBurninPeriod(int n) { burninPeriod = n; }
-  public void setOptimizeInterval(int n) { optimizeInterval = n; }   // hyper-opt: not on the GPU path yet
+  public void setOptimizeInterval(int n) { optimizeInterval = n; }   // optimizeAlpha / optimizeBeta every n sweeps
   public void setNumThreads(int n) { numThreads = Math.max(1, n); }  // = AD-LDA shards = GPUs
   public void setRandomSeed(int seed) { randomSeed = seed; }
   public void setTopicDisplay(int interval, int n) { showTopicsInterval = interval; wordsPerTopic = n; }
@@ -208,7 +214,33 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   /** estimate(): numIterations sweeps on the GPU, then z is written back into every topicSequence. */
   public void estimate() throws IOException {
     try {
-      check((int) SWEEP.invokeExact(ctx, numIterations));
+      if (optimizeInterval == 0 || numIterations <= burninPeriod) {
+        check((int) SWEEP.invokeExact(ctx, numIterations));
+      } else {
+        // Mallet's schedule: statistics on iterations > burn-in that are multiples of
+        // saveSampleInterval, optimizeAlpha + optimizeBeta on multiples of optimizeInterval
+        int width = 1;
+        for (int d = 0; d + 1 < docPtr.length; d++) width = Math.max(width, (int) (docPtr[d + 1] - docPtr[d]) + 1);
+        check((int) HYPER_BEGIN.invokeExact(ctx, width));
+        for (int iteration = 1; iteration <= numIterations; iteration++) {
+          check((int) SWEEP.invokeExact(ctx, 1));
+          if (iteration <= burninPeriod) continue;
+          if (iteration % saveSampleInterval == 0) check((int) HYPER_COLLECT.invokeExact(ctx));
+          if (iteration % optimizeInterval == 0) {
+            check((int) OPTIMIZE_ALPHA.invokeExact(ctx));
+            check((int) OPTIMIZE_BETA.invokeExact(ctx));
+            try (Arena a = Arena.ofConfined()) {
+              MemorySegment al = a.allocate(JAVA_DOUBLE, numTopics), be = a.allocate(JAVA_DOUBLE);
+              check((int) GET_ALPHA.invokeExact(ctx, al));
+              check((int) GET_BETA.invokeExact(ctx, be));
+              alpha = al.toArray(JAVA_DOUBLE);
+              alphaSum = Arrays.stream(alpha).sum();
+              beta = be.get(JAVA_DOUBLE, 0);
+              betaSum = beta * numTypes;
+            }
+          }
+        }
+      }
     } catch (RuntimeException | Error e) {
       throw e;
     } catch (Throwable t) {

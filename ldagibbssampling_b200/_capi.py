@@ -91,6 +91,13 @@ SYMBOLS = [
     ("b200lda_set_alpha", C.c_int, [_P, _P]),
     ("b200lda_get_alpha", C.c_int, [_P, _P]),
     ("b200lda_set_beta", C.c_int, [_P, C.c_double]),
+    ("b200lda_get_beta", C.c_int, [_P, C.POINTER(C.c_double)]),
+    ("b200lda_hyper_begin", C.c_int, [_P, C.c_int32]),
+    ("b200lda_hyper_collect", C.c_int, [_P]),
+    ("b200lda_hyper_buffer", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    ("b200lda_hyper_get", C.c_int, [_P, _P, _P]),
+    ("b200lda_optimize_alpha", C.c_int, [_P]),
+    ("b200lda_optimize_beta", C.c_int, [_P]),
     ("b200lda_set_sweep_counter", C.c_int, [_P, C.c_int64]),
     ("b200lda_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200lda_reset_stats", C.c_int, [_P]),
@@ -298,6 +305,36 @@ class Sampler:
 
     def set_beta(self, beta):
         self._check(self._lib.b200lda_set_beta(self._h, beta))
+
+    def beta(self):
+        out = C.c_double()
+        self._check(self._lib.b200lda_get_beta(self._h, C.byref(out)))
+        return out.value
+
+    def hyper_begin(self, width):
+        self._check(self._lib.b200lda_hyper_begin(self._h, width))
+        self._hyper_width = width
+
+    def hyper_collect(self):
+        self._check(self._lib.b200lda_hyper_collect(self._h))
+
+    def hyper_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.b200lda_hyper_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def hyper_get(self):
+        w = self._hyper_width
+        tdc = np.zeros((self.K, w), np.int32)
+        dlc = np.zeros(w, np.int32)
+        self._check(self._lib.b200lda_hyper_get(self._h, _ptr(tdc), _ptr(dlc)))
+        return tdc, dlc
+
+    def optimize_alpha(self):
+        self._check(self._lib.b200lda_optimize_alpha(self._h))
+
+    def optimize_beta(self):
+        self._check(self._lib.b200lda_optimize_beta(self._h))
 
     def set_sweep_counter(self, n):
         self._check(self._lib.b200lda_set_sweep_counter(self._h, n))

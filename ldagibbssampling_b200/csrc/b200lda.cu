@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "device_common.cuh"
+#include "hyper_kernels.cuh"
 #include "loglik_kernels.cuh"
 #include "pack_kernels.cuh"
 #include "sweep_kernel.cuh"
@@ -149,6 +150,8 @@ struct b200lda_ctx {
   double* d_partial = nullptr;  // [2 * kPartial + 2]
   uint32_t* d_hist_scratch = nullptr;
   size_t hist_scratch_bytes = 0;
+  int32_t* d_hyper = nullptr;  // [(K + 1) * hyper_width] topicDocCounts rows + docLengthCounts row
+  int hyper_width = 0, hyper_samples = 0;
 
   // state
   bool corpus_loaded = false, assigned = false, in_sweep = false, in_sync = false;
@@ -461,6 +464,7 @@ int build_doc_rows(b200lda_ctx* c, DeviceCorpus& cp) {
     const size_t need = sizeof(uint32_t) * (size_t)c->K * wpc * grid;
     if (need > c->hist_scratch_bytes) {
       dev_free(c->d_hist_scratch);
+  dev_free(c->d_hyper);
       TRY(dev_alloc(c, reinterpret_cast<void**>(&c->d_hist_scratch), need));
       c->hist_scratch_bytes = need;
     }
@@ -731,6 +735,7 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_bad);
   dev_free(c->d_partial);
   dev_free(c->d_hist_scratch);
+  dev_free(c->d_hyper);
   if (c->d_stage) cudaFree(c->d_stage);
   for (auto& e : c->ev_pool)
     if (e) cudaEventDestroy(e);
@@ -1169,6 +1174,158 @@ int b200lda_set_sweep_counter(b200lda_ctx* c, int64_t sweeps_done) {
   if (!c) return fail(B200LDA_EINVAL, "null context");
   if (sweeps_done < 0) return fail(B200LDA_EINVAL, "negative sweep counter");
   c->sweeps_done = sweeps_done;
+  return B200LDA_OK;
+}
+
+// ---- hyper-parameter optimisation --------------------------------------------------------------
+
+int b200lda_hyper_begin(b200lda_ctx* c, int32_t width) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (width <= c->corp.max_doc_len)
+    return fail(B200LDA_EINVAL, "histogram width %d must exceed the longest document (%d tokens)", width,
+                c->corp.max_doc_len);
+  const size_t cells = ((size_t)c->K + 1) * (size_t)width;
+  if (width != c->hyper_width) {
+    dev_free(c->d_hyper);
+    TRY(dev_alloc_t(c, &c->d_hyper, cells));
+    c->hyper_width = width;
+  }
+  CU(cudaMemsetAsync(c->d_hyper, 0, sizeof(int32_t) * cells, c->stream));
+  c->hyper_samples = 0;
+  return B200LDA_OK;
+}
+
+int b200lda_hyper_collect(b200lda_ctx* c) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!c->d_hyper) return fail(B200LDA_ESTATE, "call b200lda_hyper_begin first");
+  const DeviceCorpus& cp = c->corp;
+  if (cp.D > 0) {
+    k_hyper_collect<<<grid_for(c, cp.D * 32, 256), 256, 0, c->stream>>>(cp.D, c->K, c->hyper_width, cp.d_doc_ptr,
+                                                                       cp.d_row_ptr, cp.d_row_nnz, cp.d_rows, c->d_hyper);
+    c->launches += 1;
+    CU(cudaGetLastError());
+  }
+  c->hyper_samples += 1;
+  return B200LDA_OK;
+}
+
+int b200lda_hyper_buffer(b200lda_ctx* c, void** d_buf, int64_t* count) {
+  if (!c || !d_buf || !count) return fail(B200LDA_EINVAL, "null argument");
+  *d_buf = c->d_hyper;
+  *count = c->d_hyper ? (int64_t)(((size_t)c->K + 1) * (size_t)c->hyper_width) : 0;
+  return B200LDA_OK;
+}
+
+int b200lda_hyper_get(b200lda_ctx* c, int32_t* topic_doc_counts, int32_t* doc_length_counts) {
+  TRY(enter(c));
+  if (!c->d_hyper) return fail(B200LDA_ESTATE, "call b200lda_hyper_begin first");
+  const size_t w = (size_t)c->hyper_width;
+  if (topic_doc_counts)
+    CU(cudaMemcpyAsync(topic_doc_counts, c->d_hyper, sizeof(int32_t) * (size_t)c->K * w, cudaMemcpyDeviceToHost, c->stream));
+  if (doc_length_counts)
+    CU(cudaMemcpyAsync(doc_length_counts, c->d_hyper + (size_t)c->K * w, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+// ParallelTopicModel.optimizeAlpha: Dirichlet.learnParameters(alpha, topicDocCounts, docLengthCounts)
+// = Minka's fixed point on the histograms with a Gamma(shape 1.00001, scale 1) prior, 200 rounds.
+int b200lda_optimize_alpha(b200lda_ctx* c) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!c->d_hyper) return fail(B200LDA_ESTATE, "call b200lda_hyper_begin / b200lda_hyper_collect first");
+  const int K = c->K, W = c->hyper_width;
+  std::vector<int32_t> hist(((size_t)K + 1) * (size_t)W);
+  CU(cudaMemcpyAsync(hist.data(), c->d_hyper, sizeof(int32_t) * hist.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int32_t* lengths = hist.data() + (size_t)K * W;
+  const double shape = 1.00001, scale = 1.0;
+  std::vector<int> limit((size_t)K, -1);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < W; ++n)
+      if (hist[(size_t)k * W + n] > 0) limit[(size_t)k] = n;
+  std::vector<double> a = c->alpha;
+  double sum = 0.0;
+  for (double v : a) sum += v;
+  for (int it = 0; it < 200; ++it) {
+    double denom = 0.0, dg = 0.0;
+    for (int i = 1; i < W; ++i) {
+      dg += 1.0 / (sum + i - 1);
+      denom += lengths[i] * dg;
+    }
+    denom -= 1.0 / scale;
+    sum = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double old = a[(size_t)k];
+      const int32_t* h = hist.data() + (size_t)k * W;
+      double acc = 0.0;
+      dg = 0.0;
+      for (int i = 1; i <= limit[(size_t)k]; ++i) {
+        dg += 1.0 / (old + i - 1);
+        acc += h[i] * dg;
+      }
+      a[(size_t)k] = old * (acc + shape) / denom;
+      sum += a[(size_t)k];
+    }
+  }
+  for (int k = 0; k < K; ++k)
+    if (!(a[(size_t)k] > 0.0) || !std::isfinite(a[(size_t)k]))
+      return fail(B200LDA_ERANGE, "alpha optimisation diverged at topic %d (no statistics collected?)", k);
+  c->alpha = a;
+  TRY(push_alpha(c));
+  CU(cudaMemsetAsync(c->d_hyper, 0, sizeof(int32_t) * hist.size(), c->stream));  // Mallet clears the histograms
+  c->hyper_samples = 0;
+  return B200LDA_OK;
+}
+
+// ParallelTopicModel.optimizeBeta: Dirichlet.learnSymmetricConcentration on the histogram of cell
+// values of n_wk and the topic sizes n_k; 200 fixed-point rounds, each one streaming pass over n_wk.
+int b200lda_optimize_beta(b200lda_ctx* c) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  const size_t VK = (size_t)c->V * c->K;
+  std::vector<int32_t> nk((size_t)c->K);
+  CU(cudaMemcpyAsync(nk.data(), c->d_nk, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  auto digamma = [](double z) {  // recurrence + asymptotic series
+    double psi = 0.0;
+    while (z < 10.0) {
+      psi -= 1.0 / z;
+      z += 1.0;
+    }
+    const double iz = 1.0 / z, iz2 = iz * iz;
+    return psi + std::log(z) - 0.5 * iz -
+           iz2 * (1.0 / 12 - iz2 * (1.0 / 120 - iz2 * (1.0 / 252 - iz2 * (1.0 / 240 - iz2 * (1.0 / 132)))));
+  };
+  double beta_sum = c->beta * (double)c->V;
+  double* d_part = c->d_partial;  // kPartial block partials, summed on the host in a fixed order
+  std::vector<double> part((size_t)kPartial);
+  for (int it = 1; it <= 200; ++it) {
+    const double param = beta_sum / (double)c->V;
+    k_beta_numerator<<<kPartial, 256, 0, c->stream>>>(VK, c->d_nwk, param, d_part);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * kPartial, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double numerator = 0.0;
+    for (double v : part) numerator += v;
+    const double base = digamma(beta_sum);
+    double denominator = 0.0;
+    for (int k = 0; k < c->K; ++k)
+      if (nk[(size_t)k] > 0) denominator += digamma(beta_sum + (double)nk[(size_t)k]) - base;
+    if (!(denominator > 0.0) || !(numerator > 0.0)) return fail(B200LDA_ERANGE, "beta optimisation has no statistics");
+    beta_sum = param * numerator / denominator;
+  }
+  if (!(beta_sum > 0.0) || !std::isfinite(beta_sum)) return fail(B200LDA_ERANGE, "beta optimisation diverged");
+  c->beta = beta_sum / (double)c->V;
+  return B200LDA_OK;
+}
+
+int b200lda_get_beta(b200lda_ctx* c, double* beta) {
+  if (!c || !beta) return fail(B200LDA_EINVAL, "null argument");
+  *beta = c->beta;
   return B200LDA_OK;
 }
 

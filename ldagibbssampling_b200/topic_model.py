@@ -30,12 +30,12 @@ class _LocalReducer:
     """Sums the shards' exchange buffers when every shard lives in this process (several contexts,
     one per GPU or several per GPU). Device-side adds through torch; no host round trip."""
 
-    def __init__(self, samplers):
+    def __init__(self, samplers, which="exchange"):
         import torch
         self.torch = torch
         self.bufs = []
         for s in samplers:
-            ptr, n = s.exchange_buffer()
+            ptr, n = s.exchange_buffer() if which == "exchange" else s.hyper_buffer()
             dev = torch.device("cuda", s.device)
             self.bufs.append(torch.as_tensor(_DevBuf(ptr, n), device=dev))
 
@@ -61,11 +61,11 @@ class _DistReducer:
     """One process per GPU: the exchange is a torch.distributed all-reduce (NCCL over NVLink)
     enqueued on the sampler's stream between sweep_begin and sweep_end."""
 
-    def __init__(self, sampler, group=None):
+    def __init__(self, sampler, group=None, which="exchange"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
-        ptr, n = sampler.exchange_buffer()
+        ptr, n = sampler.exchange_buffer() if which == "exchange" else sampler.hyper_buffer()
         self.buf = torch.as_tensor(_DevBuf(ptr, n), device=torch.device("cuda", sampler.device))
         self.stream = torch.cuda.ExternalStream(sampler.stream(), device=torch.device("cuda", sampler.device))
 
@@ -94,6 +94,7 @@ class ParallelTopicModel:
         self.numIterations = 1000
         self.burninPeriod = 200
         self.optimizeInterval = 50
+        self.saveSampleInterval = 10
         self.showTopicsInterval = 50
         self.wordsPerTopic = 7
         self.numThreads = 1
@@ -263,21 +264,48 @@ class ParallelTopicModel:
         if self._dirty:
             self._pull_assignments()
             self._build_device_state()
-        if self.optimizeInterval != 0:
-            warnings.warn("hyper-parameter optimisation (setOptimizeInterval) is not on the GPU path yet; "
-                          "alpha and beta stay fixed (SURVEY.md §8(f) row 2)", RuntimeWarning, stacklevel=2)
         n = self.numIterations
         world, my_rank = self._world()
-        if world == 1:
+        optimizing = self.optimizeInterval != 0 and n > self.burninPeriod
+        if world == 1 and not optimizing:
             self._samplers[0].sweep(n)
         else:
-            reducer = self._get_reducer()
-            for _ in range(n):
+            reducer = self._get_reducer() if world > 1 else None
+            hyper_reducer = None
+            if optimizing:
+                width = int(np.diff(self._doc_ptr).max()) + 1 if len(self._doc_ptr) > 1 else 1
                 for s in self._samplers:
-                    s.sweep_begin()
-                reducer(self._samplers)
-                for s in self._samplers:
-                    s.sweep_end()
+                    s.hyper_begin(width)
+                if world > 1:
+                    hyper_reducer = (_DistReducer(self._samplers[0], self.process_group, which="hyper")
+                                     if my_rank is not None else _LocalReducer(self._samplers, which="hyper"))
+            # Mallet's estimate(): iteration counts from 1 on every call; statistics are collected on
+            # iterations > burninPeriod that are multiples of saveSampleInterval, alpha and beta are
+            # re-estimated on those that are multiples of optimizeInterval.
+            for iteration in range(1, n + 1):
+                if world == 1:
+                    self._samplers[0].sweep(1)
+                else:
+                    for s in self._samplers:
+                        s.sweep_begin()
+                    reducer(self._samplers)
+                    for s in self._samplers:
+                        s.sweep_end()
+                if not optimizing or iteration <= self.burninPeriod:
+                    continue
+                if iteration % self.saveSampleInterval == 0:
+                    for s in self._samplers:
+                        s.hyper_collect()
+                if iteration % self.optimizeInterval == 0:
+                    if hyper_reducer is not None:
+                        hyper_reducer(self._samplers)
+                    for s in self._samplers:
+                        s.optimize_alpha()
+                        s.optimize_beta()
+                    self.alpha = self._samplers[0].alpha()
+                    self.alphaSum = float(self.alpha.sum())
+                    self.beta = self._samplers[0].beta()
+                    self.betaSum = self.beta * self.numTypes
             for s in self._samplers:
                 s.synchronize()
         self._iterationsSoFar += n

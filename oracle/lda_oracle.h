@@ -127,6 +127,15 @@ void mallet_infer(const mallet_model* m, const int32_t* words, int32_t n, int32_
                   int32_t thinning, int32_t burn_in, int32_t seed, double* theta);
 int64_t mallet_num_tokens(const mallet_model* m);
 
+/* Hyper-parameter optimisation pieces of cc.mallet.types.Dirichlet. */
+double oracle_digamma(double z);
+double oracle_learn_parameters(double* parameters, int32_t K, const int32_t* observations, int32_t width,
+                               const int32_t* observation_lengths, double shape, double scale,
+                               int32_t num_iterations);
+double oracle_learn_symmetric_concentration(const int64_t* count_histogram, int64_t n_counts,
+                                            const int64_t* observation_lengths, int64_t n_lengths,
+                                            int32_t num_dimensions, double current_value);
+
 #ifdef __cplusplus
 }
 #endif

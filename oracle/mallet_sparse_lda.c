@@ -634,3 +634,109 @@ void mallet_infer(const mallet_model* m, const int32_t* words, int32_t n, int32_
   free(coef);
   free(scores);
 }
+
+/* ---- hyper-parameter optimisation (enabled by setOptimizeInterval(20) at
+ * reference cmu_ron/TrainAndPredict.java:163, cmu/TrainAndPredict.java:261) -------------------- */
+
+/* Mallet's Dirichlet.digamma: recurrence up to z >= 6-ish then the asymptotic series. */
+double oracle_digamma(double z) {
+  const double EULER_MASCHERONI = -0.5772156649015328606065121;
+  const double DIGAMMA_COEF_1 = 1.0 / 12, DIGAMMA_COEF_2 = 1.0 / 120, DIGAMMA_COEF_3 = 1.0 / 252,
+               DIGAMMA_COEF_4 = 1.0 / 240, DIGAMMA_COEF_5 = 1.0 / 132, DIGAMMA_COEF_6 = 691.0 / 32760,
+               DIGAMMA_COEF_7 = 1.0 / 12;
+  const double DIGAMMA_LARGE = 9.5, DIGAMMA_SMALL = .000001;
+  double psi = 0;
+  if (z < DIGAMMA_SMALL) return EULER_MASCHERONI - (1 / z);
+  while (z < DIGAMMA_LARGE) {
+    psi -= 1 / z;
+    z++;
+  }
+  double invZ = 1 / z, invZSquared = invZ * invZ;
+  psi += log(z) - .5 * invZ -
+         invZSquared * (DIGAMMA_COEF_1 - invZSquared * (DIGAMMA_COEF_2 - invZSquared * (DIGAMMA_COEF_3 -
+         invZSquared * (DIGAMMA_COEF_4 - invZSquared * (DIGAMMA_COEF_5 - invZSquared * (DIGAMMA_COEF_6 -
+         invZSquared * DIGAMMA_COEF_7))))));
+  return psi;
+}
+
+/* Dirichlet.learnParameters(parameters, observations, observationLengths, 1.00001, 1.0, 200):
+ * Minka/Wallach fixed point on histograms. observations is K rows of `width` counts
+ * (observations[k][n] = documents in which topic k occurs n times), observationLengths[n] =
+ * documents of length n. parameters (alpha) is updated in place; returns their sum. */
+double oracle_learn_parameters(double* parameters, int32_t K, const int32_t* observations, int32_t width,
+                               const int32_t* observation_lengths, double shape, double scale,
+                               int32_t num_iterations) {
+  double parameters_sum = 0;
+  for (int32_t k = 0; k < K; ++k) parameters_sum += parameters[k];
+  int32_t* non_zero_limits = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  for (int32_t k = 0; k < K; ++k) {
+    non_zero_limits[k] = -1;
+    const int32_t* h = observations + (size_t)k * width;
+    for (int32_t n = 0; n < width; ++n)
+      if (h[n] > 0) non_zero_limits[k] = n;
+  }
+  for (int32_t it = 0; it < num_iterations; ++it) {
+    double denominator = 0, current_digamma = 0;
+    for (int32_t i = 1; i < width; ++i) {
+      current_digamma += 1 / (parameters_sum + i - 1);
+      denominator += observation_lengths[i] * current_digamma;
+    }
+    denominator -= 1 / scale;
+    parameters_sum = 0;
+    for (int32_t k = 0; k < K; ++k) {
+      const int32_t limit = non_zero_limits[k];
+      const double old = parameters[k];
+      const int32_t* h = observations + (size_t)k * width;
+      double acc = 0;
+      current_digamma = 0;
+      for (int32_t i = 1; i <= limit; ++i) {
+        current_digamma += 1 / (old + i - 1);
+        acc += h[i] * current_digamma;
+      }
+      parameters[k] = old * (acc + shape) / denominator;
+      parameters_sum += parameters[k];
+    }
+  }
+  free(non_zero_limits);
+  return parameters_sum;
+}
+
+/* Dirichlet.learnSymmetricConcentration(countHistogram, observationLengths, numDimensions,
+ * currentValue): count_histogram[c] = (type, topic) cells holding c tokens, observation_lengths[n]
+ * = topics holding n tokens; returns the new betaSum. */
+double oracle_learn_symmetric_concentration(const int64_t* count_histogram, int64_t n_counts,
+                                            const int64_t* observation_lengths, int64_t n_lengths,
+                                            int32_t num_dimensions, double current_value) {
+  int64_t largest_non_zero_count = 0;
+  for (int64_t i = 0; i < n_counts; ++i)
+    if (count_histogram[i] > 0) largest_non_zero_count = i;
+  int64_t* non_zero_length_index = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_lengths > 0 ? n_lengths : 1));
+  int64_t dense_size = 0;
+  for (int64_t i = 0; i < n_lengths; ++i)
+    if (observation_lengths[i] > 0) non_zero_length_index[dense_size++] = i;
+  for (int iteration = 1; iteration <= 200; ++iteration) {
+    const double current_parameter = current_value / num_dimensions;
+    double current_digamma = 0, numerator = 0;
+    for (int64_t index = 1; index <= largest_non_zero_count; ++index) {
+      current_digamma += 1.0 / (current_parameter + index - 1);
+      numerator += count_histogram[index] * current_digamma;
+    }
+    current_digamma = 0;
+    double denominator = 0;
+    int64_t previous_length = 0;
+    const double cached_digamma = oracle_digamma(current_value);
+    for (int64_t di = 0; di < dense_size; ++di) {
+      const int64_t length = non_zero_length_index[di];
+      if (length - previous_length > 20) {
+        current_digamma = oracle_digamma(current_value + length) - cached_digamma;
+      } else {
+        for (int64_t index = previous_length; index < length; ++index) current_digamma += 1.0 / (current_value + index);
+      }
+      denominator += current_digamma * observation_lengths[length];
+      previous_length = length; /* (Mallet omits this update; with it the shortcut is exact) */
+    }
+    current_value = current_parameter * numerator / denominator;
+  }
+  free(non_zero_length_index);
+  return current_value;
+}

@@ -98,6 +98,12 @@ def lib():
     L.mallet_get_topic_probabilities.argtypes = [C.c_void_p, C.c_int64, _f64p]
     L.mallet_infer.argtypes = [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, _f64p]
+    L.oracle_digamma.restype = C.c_double
+    L.oracle_digamma.argtypes = [C.c_double]
+    L.oracle_learn_parameters.restype = C.c_double
+    L.oracle_learn_parameters.argtypes = [_f64p, C.c_int32, _i32p, C.c_int32, _i32p, C.c_double, C.c_double, C.c_int32]
+    L.oracle_learn_symmetric_concentration.restype = C.c_double
+    L.oracle_learn_symmetric_concentration.argtypes = [_i64p, C.c_int64, _i64p, C.c_int64, C.c_int32, C.c_double]
     L.mallet_num_tokens.restype = C.c_int64
     L.mallet_num_tokens.argtypes = [C.c_void_p]
     _lib = L
@@ -278,6 +284,27 @@ def phi(nwk, nk, beta):
     lib().oracle_phi(V, K, np.ascontiguousarray(nwk, np.int32).reshape(-1),
                      np.ascontiguousarray(nk, np.int32), beta, out.reshape(-1))
     return out
+
+
+def digamma(x):
+    return float(lib().oracle_digamma(x))
+
+
+def learn_parameters(alpha, topic_doc_counts, doc_length_counts, shape=1.00001, scale=1.0, iterations=200):
+    """Dirichlet.learnParameters on histograms; returns (new alpha, alphaSum)."""
+    a = np.array(alpha, np.float64, copy=True)
+    obs = np.ascontiguousarray(topic_doc_counts, np.int32)
+    K, width = obs.shape
+    lens = np.ascontiguousarray(doc_length_counts, np.int32)
+    assert len(lens) == width
+    s = lib().oracle_learn_parameters(a, K, obs.reshape(-1), width, lens, shape, scale, iterations)
+    return a, float(s)
+
+
+def learn_symmetric_concentration(count_histogram, topic_size_histogram, num_types, beta_sum):
+    ch = np.ascontiguousarray(count_histogram, np.int64)
+    th = np.ascontiguousarray(topic_size_histogram, np.int64)
+    return float(lib().oracle_learn_symmetric_concentration(ch, len(ch), th, len(th), num_types, beta_sum))
 
 
 # ---- Mallet-faithful model ------------------------------------------------------------------

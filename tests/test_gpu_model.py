@@ -189,13 +189,62 @@ def test_parallel_topic_model_mirror_runs_the_reference_flow(oracle, tmp_path):
     assert len(rows) == K
     ar = rows[0].split("\t")
     assert int(ar[0]) == 0 and float(ar[1]) == pytest.approx(ALPHA) and len(ar[2].split(" ")) >= 1
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        model.setOptimizeInterval(20)
-        model.setNumIterations(1)
-        model.estimate()
-        assert any("hyper-parameter" in str(x.message) for x in w)
+    # setOptimizeInterval(20) as the reference sets it (cmu_ron/TrainAndPredict.java:163): alpha becomes
+    # asymmetric and beta moves once iterations pass the burn-in
+    model.setBurninPeriod(10)
+    model.setOptimizeInterval(20)
+    model.setNumIterations(40)
+    a0, b0 = model.alpha.copy(), model.beta
+    model.estimate()
+    assert model.alpha.shape == (K,) and np.all(model.alpha > 0) and np.ptp(model.alpha) > 0
+    assert not np.allclose(model.alpha, a0) and model.beta != b0 and model.beta > 0
+    assert abs(model.alphaSum - model.alpha.sum()) < 1e-12
+    th = model.getTopicProbabilities(model.data[0].topicSequence)
+    assert abs(th.sum() - 1) < 1e-12
     model.close()
+
+
+def test_hyper_parameter_optimisation_matches_oracle(oracle):
+    """optimizeAlpha / optimizeBeta: device histograms equal a recount from the n_dk rows, and the
+    fixed points equal the oracle's restatement of Dirichlet.learnParameters /
+    learnSymmetricConcentration on the same statistics."""
+    L = _L()
+    D, V, K = 1500, 400, 12
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 8, 39)
+    s = L.Sampler(K, V, ALPHA * K, BETA, seed=2, mode=L.MODE_DEFERRED)
+    s.load_corpus(dp, tok)
+    s.init_assignments(None)
+    s.sweep(30)
+    width = int(np.diff(dp).max()) + 1
+    with pytest.raises(L.B200LDAError):
+        s.hyper_begin(width - 1)                      # must exceed the longest document
+    s.hyper_begin(width)
+    want_tdc = np.zeros((K, width), np.int32)
+    want_dlc = np.zeros(width, np.int32)
+    for _ in range(2):                                # two saved samples, as Mallet accumulates
+        s.sweep(5)
+        s.hyper_collect()
+        rp, topic, cnt = s.ndk_csr()
+        np.add.at(want_tdc, (topic, cnt), 1)
+        np.add.at(want_dlc, np.diff(dp), 1)
+    tdc, dlc = s.hyper_get()
+    assert np.array_equal(tdc, want_tdc) and np.array_equal(dlc, want_dlc)
+    a0 = s.alpha()
+    s.optimize_alpha()
+    want_alpha, want_sum = oracle.learn_parameters(a0, tdc, dlc)
+    assert np.allclose(s.alpha(), want_alpha, rtol=1e-12, atol=0)
+    assert np.ptp(s.alpha()) > 0
+    tdc2, dlc2 = s.hyper_get()
+    assert tdc2.sum() == 0 and dlc2.sum() == 0        # histograms cleared, as Mallet does
+    nwk, nk = s.nwk(), s.nk()
+    want_beta = oracle.learn_symmetric_concentration(np.bincount(nwk[nwk > 0]), np.bincount(nk), V, BETA * V) / V
+    s.optimize_beta()
+    assert abs(s.beta() - want_beta) <= 1e-9 * want_beta   # digamma differences vs running sums
+    s.sweep(3)                                        # the chain continues under the new alpha, beta
+    nwk, nk = oracle.count(dp, tok, s.assignments(), V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    ll = oracle.loglik(dp, tok, s.assignments(), V, K, s.alpha(), s.beta())
+    assert abs(s.loglik() - ll) <= 1e-9 * abs(ll)
 
 
 def test_mirror_with_two_threads_is_two_shards(oracle):

@@ -264,3 +264,30 @@ def test_inferencers_return_distributions(oracle):
     assert abs(th2.sum() - 1) < 1e-12
     assert np.abs(th2 - th).sum() < 0.6
     m.close()
+
+
+def test_hyper_parameter_fixed_points_recover_known_parameters(oracle):
+    """Dirichlet.learnParameters / learnSymmetricConcentration restatements: digamma against scipy,
+    and maximum-likelihood recovery of the parameters that generated the histograms."""
+    from scipy.special import digamma
+    for x in (1e-7, 0.01, 0.5, 1.0, 5.5, 100.0, 1e6):
+        assert abs(oracle.digamma(x) - digamma(x)) <= 1e-6 * max(1.0, abs(digamma(x)))
+    rng = np.random.default_rng(0)
+    K, D = 5, 6000
+    a_true = np.array([0.5, 1.0, 0.2, 2.0, 0.8])
+    lens = rng.integers(20, 80, D)
+    width = int(lens.max()) + 1
+    tdc = np.zeros((K, width), np.int32)
+    dlc = np.zeros(width, np.int32)
+    for d in range(D):
+        c = rng.multinomial(lens[d], rng.dirichlet(a_true))
+        dlc[lens[d]] += 1
+        tdc[np.arange(K), c] += 1
+    a, s = oracle.learn_parameters(np.full(K, 1.0), tdc, dlc)
+    assert abs(s - a.sum()) < 1e-12 and np.allclose(a, a_true, rtol=0.08)
+    # symmetric concentration: V-dimensional multinomials per topic drawn from Dirichlet(beta)
+    V, T, beta_true = 300, 40, 0.05
+    sizes = rng.integers(2000, 6000, T)
+    cells = np.concatenate([rng.multinomial(n, rng.dirichlet(np.full(V, beta_true))) for n in sizes])
+    got = oracle.learn_symmetric_concentration(np.bincount(cells[cells > 0]), np.bincount(sizes), V, 1.0 * V) / V
+    assert abs(got - beta_true) < 0.15 * beta_true
