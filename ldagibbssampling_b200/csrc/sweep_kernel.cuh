@@ -12,10 +12,14 @@
 //     resolved by a fan-out-32 search = one coalesced 128-byte line per level;
 //   * randomness: Philox keyed by (seed; global token, sweep), 32 tokens per warp batch, one
 //     lane each, so the RNG costs ~2 instructions per token;
-//   * count moves: one pass over the part of the 16-bit row between the slot that empties and
-//     the slot that appears, integer RED atomics on n_wk / n_k deltas.
+//   * count moves: the row edit happens in registers (one shuffle per tile) for rows of up to
+//     kRegTiles tiles, integer RED atomics carry the n_wk / n_k moves.
+// The kernel is instruction-issue bound (profiles/r01_sweep_v3_ncu_summary.txt), so the token step
+// is specialised on the number of 32-slot tiles of the row: token_step_tiles<NT> is straight-line
+// code (full tiles unpredicated, prefixes in registers, no inner loops); token_step_generic keeps
+// the loop form for rows wider than kRegTiles tiles.
 // Documents are visited through doc_order (longest first); the host launches the kernel once per
-// document class so that short documents get small per-warp rows and therefore high occupancy.
+// row-width class so that per-warp shared memory follows the row width.
 // MODE_UPDATE serves LIVE (LIVE=true: n_wk read through L2 and written in place) and DEFERRED
 // (LIVE=false: frozen n_wk through the read-only path, moves go to a second buffer);
 // MODE_FROZEN moves nothing (north-star parity mode).
@@ -27,7 +31,7 @@ namespace b200lda {
 enum { MODE_UPDATE = 0, MODE_FROZEN = 1 };
 
 struct SweepParams {
-  const int32_t* doc_order;   // [D] document ids, class by class, longest first
+  const int32_t* doc_order;   // [D] document ids, longest first
   int64_t order_begin, order_end;  // this launch's slice of doc_order
   const int64_t* doc_ptr;     // [D+1] token offsets (document order)
   const int32_t* tok_word;    // [N]
@@ -37,7 +41,7 @@ struct SweepParams {
   int32_t* row_nnz;           // [D]
   uint32_t* rows;             // packed (topic << 16 | count), ascending topic
   const int32_t* nwk_read;    // [V*K]
-  int32_t* nwk_write;         // [V*K] (== nwk_read when LIVE)
+  int32_t* nwk_write;         // [V*K] (== nwk_read when LIVE; nullptr: no count writes)
   int32_t* nk_delta;          // [K]
   const float* invden;        // [K]  1 / (n_k + V beta)
   const float* ab;            // [K]  alpha_k * invden_k
@@ -62,10 +66,222 @@ struct SweepParams {
 #ifndef B200LDA_SWEEP_GROUP
 #define B200LDA_SWEEP_GROUP 4  // measured on B200: 4 > 3 > 2 > 1 (profiles/r01_tuning.md)
 #endif
-constexpr int kGroup = B200LDA_SWEEP_GROUP;  // tiles whose gathers are in flight together
+constexpr int kGroup = B200LDA_SWEEP_GROUP;  // generic path: tiles whose gathers are in flight together
+constexpr int kRegTiles = 4;                 // rows of up to 4 tiles (128 slots) take the register path
 
 // Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot.
 constexpr int kSmemBytesPerSlot = 8;
+
+#ifndef B200LDA_SWEEP_MIN_CTAS
+#define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
+#endif
+
+// Per-warp constants and counters shared by the token-step variants.
+struct WarpCtx {
+  int lane;
+  float m1, m2, m4, m8, m16;  // Kogge-Stone lane masks: v = y*m + v is "if (lane >= d) v += y" in one FFMA
+  float beta_f;
+  int excl;
+  int K;
+  uint32_t* slots;   // this warp's row in shared memory
+  float* pref;       // this warp's prefix scratch (generic path)
+  const float* s_tab;  // [invden | ab] in shared memory (TABLES_IN_SMEM)
+  unsigned st_moved, st_prior;
+};
+
+__device__ __forceinline__ float scan_tile(float a, const WarpCtx& c) {
+  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), c.m1, a);
+  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), c.m2, a);
+  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), c.m4, a);
+  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), c.m8, a);
+  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), c.m16, a);
+  return a;
+}
+
+// Prior bucket: skip the own-token mass delta at topic o, then the fan-out-32 search.
+__device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int w, int o, float y, float delta) {
+  const float* prow = p.prior + (size_t)w * p.layout.stride;
+  const float po = __ldg(prow + o);  // level 0 sits at offset 0
+  const float pod = fsub(po, delta);
+  const float s = (y < pod) ? y : fadd(y, delta);
+  int block = 0;
+  for (int lev = p.layout.nlev - 1; lev >= 0; --lev) {
+    const int lo = block << 5;
+    const int nvalid = min(32, p.layout.size[lev] - lo);
+    float v = 0.0f;
+    if (lane < nvalid) v = __ldg(prow + p.layout.off[lev] + lo + lane);
+    const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
+    block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
+  }
+  return block;
+}
+
+__device__ __forceinline__ void count_moves(const SweepParams& p, int lane, int w, int K, int o, int newt) {
+  // word-topic and topic totals: integer RED atomics (order-independent sums)
+  if (lane == 0 && p.nwk_write != nullptr) {
+    int32_t* wrow = p.nwk_write + (size_t)w * K;
+    atomicAdd(wrow + o, -1);
+    atomicAdd(wrow + newt, 1);
+    atomicAdd(p.nk_delta + o, -1);
+    atomicAdd(p.nk_delta + newt, 1);
+  }
+}
+
+// ---- register path: rows that fit NT tiles with room for one more slot (nnz + 1 <= 32 NT) -------
+// Tiles 0 .. NT-2 are full, so only the last tile is predicated; prefixes stay in registers; the
+// row edit is a one-slot shift done with shuffles on the row registers, then stored back.
+template <int NT, int MODE, bool LIVE, bool TS>
+__device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
+                                                float qw) {
+  const int lane = c.lane;
+  const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
+  const int last_n = nnz - 32 * (NT - 1);  // active lanes of the last tile, 0..31
+  uint32_t sv[NT];
+  int nv[NT];
+#pragma unroll
+  for (int g = 0; g < NT; ++g) {
+    if (g < NT - 1 || lane < last_n) {
+      sv[g] = c.slots[(g << 5) + lane];
+      const int32_t* cell = nrow + (sv[g] >> 16);
+      nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
+    } else {
+      sv[g] = 0u;  // count 0 => weight exactly 0
+      nv[g] = 0;
+    }
+  }
+  float P[NT];
+  float carry = 0.0f;
+  int myjo = -1;
+#pragma unroll
+  for (int g = 0; g < NT; ++g) {
+    const int topic = (int)(sv[g] >> 16);
+    const bool is_old = (topic == o) && (g < NT - 1 || lane < last_n);
+    if (is_old) myjo = (g << 5) + lane;
+    const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
+    const int n = max(nv[g] - ((int)is_old & c.excl), 0);
+    const float inv = TS ? c.s_tab[topic] : __ldg(p.invden + topic);
+    float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
+    a = scan_tile(a, c);
+    P[g] = fadd(carry, a);
+    carry = __shfl_sync(kFullMask, P[g], 31);
+  }
+  const int jo = __reduce_max_sync(kFullMask, myjo);
+  // A = inclusive prefix at slot nnz-1: in the last tile unless that tile is empty
+  float A;
+  if (NT == 1) {
+    A = __shfl_sync(kFullMask, P[0], (nnz - 1) & 31);
+  } else {
+    const float pl = last_n > 0 ? P[NT - 1] : P[NT - 2];
+    A = __shfl_sync(kFullMask, pl, (nnz - 1) & 31);
+  }
+  float delta = TS ? c.s_tab[c.K + o] : __ldg(p.ab + o);
+  delta = c.excl ? delta : 0.0f;
+  float qp = fsub(qw, delta);
+  qp = qp < 0.0f ? 0.0f : qp;
+  const float x = fmul(u, fadd(A, qp));
+
+  int newt;
+  int jn = -1;  // slot of newt when it already has one
+  if (x < A) {
+    jn = nnz - 1;
+#pragma unroll
+    for (int g = NT - 1; g >= 0; --g) {  // descending, so the lowest tile with a hit wins
+      const bool in = (g < NT - 1) || (lane < last_n);
+      const unsigned b = __ballot_sync(kFullMask, in && (P[g] > x));
+      if (b) jn = (g << 5) + __ffs(b) - 1;
+    }
+    // topic of slot jn: it sits in tile jn >> 5, lane jn & 31
+    uint32_t sj = 0u;
+#pragma unroll
+    for (int g = 0; g < NT; ++g) {
+      const uint32_t v = __shfl_sync(kFullMask, sv[g], jn & 31);
+      if ((jn >> 5) == g) sj = v;
+    }
+    newt = (int)(sj >> 16);
+  } else {
+    ++c.st_prior;
+    newt = prior_search(p, lane, w, o, fsub(x, A), delta);
+  }
+
+  if (MODE == MODE_UPDATE && newt != o) {
+    ++c.st_moved;
+    int pos = 0;  // #slots with topic < newt (old slot still present); only needed when newt is new to the row
+    if (jn < 0) {
+#pragma unroll
+      for (int g = 0; g < NT; ++g) {
+        const bool in = (g < NT - 1) || (lane < last_n);
+        const int topic = in ? (int)(sv[g] >> 16) : 0x7fffffff;
+        pos += __popc(__ballot_sync(kFullMask, topic < newt));
+        const unsigned eq = __ballot_sync(kFullMask, topic == newt);
+        if (eq) jn = (g << 5) + __ffs(eq) - 1;
+      }
+    }
+    // the old slot's count decides whether the slot disappears
+    uint32_t so = 0u;
+#pragma unroll
+    for (int g = 0; g < NT; ++g) {
+      const uint32_t v = __shfl_sync(kFullMask, sv[g], jo & 31);
+      if ((jo >> 5) == g) so = v;
+    }
+    const bool del = (so & 0xffffu) == 1u;
+    // destinations [up_lo, up_hi] take the slot below them, [dn_lo, dn_hi] the slot above; ins gets the new slot
+    int up_lo = 1, up_hi = 0, dn_lo = 1, dn_hi = 0, ins = -1;
+    if (jn >= 0) {
+      if (del) {
+        dn_lo = jo;
+        dn_hi = nnz - 2;
+      }
+    } else if (!del) {
+      up_lo = pos + 1;
+      up_hi = nnz;
+      ins = pos;
+    } else if (pos <= jo) {
+      up_lo = pos + 1;
+      up_hi = jo;
+      ins = pos;
+    } else {
+      dn_lo = jo;
+      dn_hi = pos - 2;
+      ins = pos - 1;
+    }
+    const uint32_t fresh = ((uint32_t)newt << 16) | 1u;
+    // count edits first (they travel with the slots when those shift); sv keeps what shared memory holds
+    uint32_t ev[NT];
+#pragma unroll
+    for (int g = 0; g < NT; ++g) {
+      const int j = (g << 5) + lane;
+      ev[g] = sv[g] + (j == jn ? 1u : 0u) - ((j == jo && !del) ? 1u : 0u);
+    }
+    if (up_hi >= up_lo) {
+      uint32_t below31 = 0u;  // lane 31 of the tile below
+#pragma unroll
+      for (int g = 0; g < NT; ++g) {
+        const int j = (g << 5) + lane;
+        uint32_t prev = __shfl_up_sync(kFullMask, ev[g], 1);
+        if (lane == 0) prev = below31;
+        below31 = __shfl_sync(kFullMask, ev[g], 31);
+        uint32_t nvl = (j >= up_lo && j <= up_hi) ? prev : ev[g];
+        if (j == ins) nvl = fresh;
+        if (nvl != sv[g]) c.slots[j] = nvl;
+      }
+    } else {  // a downward shift, a bare replacement (empty range, ins >= 0) or count edits only
+#pragma unroll
+      for (int g = NT - 1; g >= 0; --g) {
+        const int j = (g << 5) + lane;
+        uint32_t next = __shfl_down_sync(kFullMask, ev[g], 1);
+        const uint32_t above0 = (g + 1 < NT) ? __shfl_sync(kFullMask, ev[g + 1 < NT ? g + 1 : g], 0) : 0u;
+        if (lane == 31) next = above0;
+        uint32_t nvl = (j >= dn_lo && j <= dn_hi) ? next : ev[g];
+        if (j == ins) nvl = fresh;
+        if (nvl != sv[g]) c.slots[j] = nvl;
+      }
+    }
+    nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
+    __syncwarp();
+    count_moves(p, lane, w, c.K, o, newt);
+  }
+  return newt;
+}
 
 // Rows [a, b) move one slot up (to [a+1, b+1)); chunks from the top so nothing is overwritten.
 __device__ __forceinline__ void row_shift_up(uint32_t* slots, int a, int b, int lane) {
@@ -90,9 +306,127 @@ __device__ __forceinline__ void row_shift_down(uint32_t* slots, int a, int b, in
   }
 }
 
-#ifndef B200LDA_SWEEP_MIN_CTAS
-#define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
-#endif
+// ---- generic path: rows of any width, loop form ----------------------------------------------------
+template <int MODE, bool LIVE, bool TS>
+__device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
+                                               float qw) {
+  const int lane = c.lane;
+  uint32_t* slots = c.slots;
+  float* pref = c.pref;
+  const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
+  // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any is
+  // consumed, so a wide row pays one memory latency per group, not per tile.
+  const int ntiles = (nnz + 31) >> 5;
+  float carry = 0.0f, P = 0.0f;
+  int jo = 0;
+  for (int t0 = 0; t0 < ntiles; t0 += kGroup) {
+    uint32_t sv[kGroup];
+    int nv[kGroup];
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) {
+      const int j = ((t0 + g) << 5) + lane;
+      sv[g] = 0u;
+      nv[g] = 0;
+      if (j < nnz) {
+        sv[g] = slots[j];
+        const int32_t* cell = nrow + (sv[g] >> 16);
+        nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) {
+      if (t0 + g < ntiles) {
+        const int j = ((t0 + g) << 5) + lane;
+        const bool act = j < nnz;
+        const int topic = (int)(sv[g] >> 16);
+        const bool is_old = act && (topic == o);
+        const unsigned bo = __ballot_sync(kFullMask, is_old);
+        if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
+        const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
+        const int n = max(nv[g] - ((int)is_old & c.excl), 0);
+        const float inv = TS ? c.s_tab[topic] : __ldg(p.invden + topic);
+        float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);  // cc == 0 past nnz
+        a = scan_tile(a, c);
+        P = fadd(carry, a);
+        pref[j] = P;
+        carry = __shfl_sync(kFullMask, P, 31);
+      }
+    }
+  }
+  const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
+  float delta = TS ? c.s_tab[c.K + o] : __ldg(p.ab + o);
+  delta = c.excl ? delta : 0.0f;
+  float qp = fsub(qw, delta);
+  qp = qp < 0.0f ? 0.0f : qp;
+  const float x = fmul(u, fadd(A, qp));
+
+  int newt;
+  int jn = -1;
+  if (x < A) {
+    jn = nnz - 1;
+    __syncwarp();
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int j = (tile << 5) + lane;
+      const bool hit = (j < nnz) && (pref[j] > x);
+      const unsigned b = __ballot_sync(kFullMask, hit);
+      if (b) {
+        jn = (tile << 5) + __ffs(b) - 1;
+        break;
+      }
+    }
+    newt = (int)(slots[jn] >> 16);
+  } else {
+    ++c.st_prior;
+    newt = prior_search(p, lane, w, o, fsub(x, A), delta);
+  }
+
+  if (MODE == MODE_UPDATE && newt != o) {
+    ++c.st_moved;
+    // Where does newt live (or go) in the row as it stands, old slot still present?
+    int pos = 0;
+    if (jn < 0) {
+      for (int tile = 0; (tile << 5) < nnz; ++tile) {
+        const int j = (tile << 5) + lane;
+        const bool act = j < nnz;
+        const int topic = act ? (int)(slots[j] >> 16) : 0x7fffffff;
+        const unsigned less = __ballot_sync(kFullMask, topic < newt);
+        const unsigned eq = __ballot_sync(kFullMask, topic == newt);
+        pos += __popc(less);
+        if (eq) jn = (tile << 5) + __ffs(eq) - 1;
+        if (eq || less != kFullMask) break;
+      }
+    }
+    const uint32_t so = slots[jo];
+    const bool del = (so & 0xffffu) == 1u;
+    __syncwarp();
+    if (jn >= 0) {                 // newt already has a slot: bump it
+      if (lane == 0) {
+        slots[jn] += 1u;
+        if (!del) slots[jo] = so - 1u;
+      }
+      if (del) {                   // ... and close the gap the old topic leaves
+        __syncwarp();
+        row_shift_down(slots, jo + 1, nnz, lane);
+        --nnz;
+      }
+    } else if (!del) {             // new slot, old one stays
+      if (lane == 0) slots[jo] = so - 1u;
+      __syncwarp();
+      row_shift_up(slots, pos, nnz, lane);
+      if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
+      ++nnz;
+    } else if (pos <= jo) {        // old slot empties, new one appears below it
+      row_shift_up(slots, pos, jo, lane);
+      if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
+    } else {                       // ... or above it
+      row_shift_down(slots, jo + 1, pos, lane);
+      if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
+    }
+    __syncwarp();
+    count_moves(p, lane, w, c.K, o, newt);
+  }
+  return newt;
+}
 
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(const SweepParams p) {
@@ -104,9 +438,6 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
 
   float* s_tab = reinterpret_cast<float*>(smem_raw);
   const int tab_floats = TABLES_IN_SMEM ? 2 * K : 0;
-  uint32_t* slots = reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)warp * p.slot_cap;
-  float* pref = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(s_tab + tab_floats) +
-                                         (size_t)nwarps * p.slot_cap) + (size_t)warp * p.slot_cap;
   if (TABLES_IN_SMEM) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       s_tab[k] = p.invden[k];
@@ -114,12 +445,24 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
     }
     __syncthreads();
   }
-  // fp32 masks that make the Kogge-Stone step "if (lane >= d) v += y" one FFMA: v = y*m + v is
-  // exactly v + y (m = 1, one rounding) or exactly v (m = 0).
-  const float m1 = lane >= 1 ? 1.0f : 0.0f, m2 = lane >= 2 ? 1.0f : 0.0f, m4 = lane >= 4 ? 1.0f : 0.0f,
-              m8 = lane >= 8 ? 1.0f : 0.0f, m16 = lane >= 16 ? 1.0f : 0.0f;
+  WarpCtx c;
+  c.lane = lane;
+  c.m1 = lane >= 1 ? 1.0f : 0.0f;
+  c.m2 = lane >= 2 ? 1.0f : 0.0f;
+  c.m4 = lane >= 4 ? 1.0f : 0.0f;
+  c.m8 = lane >= 8 ? 1.0f : 0.0f;
+  c.m16 = lane >= 16 ? 1.0f : 0.0f;
+  c.beta_f = p.beta_f;
+  c.excl = p.exclude_self;
+  c.K = K;
+  c.slots = reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)warp * p.slot_cap;
+  c.pref = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)nwarps * p.slot_cap) +
+           (size_t)warp * p.slot_cap;
+  c.s_tab = s_tab;
+  c.st_moved = 0;
+  c.st_prior = 0;
+  uint32_t* slots = c.slots;
 
-  const float beta_f = p.beta_f;
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
   const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
 
@@ -138,6 +481,7 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
       int nnz = p.row_nnz[d];
       for (int j = lane; j < nnz; j += 32) slots[j] = p.rows[rp + j];
       __syncwarp();
+      unsigned doc_nnz = 0;
 
       for (int64_t base = tb; base < te; base += 32) {
         const int64_t i = base + lane;
@@ -161,152 +505,14 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
           const int o = __shfl_sync(kFullMask, o_l, t);
           const float u = __shfl_sync(kFullMask, u_l, t);
           const float qw = __shfl_sync(kFullMask, q_l, t);
-          const int32_t* nrow = p.nwk_read + (size_t)w * K;
-          st_nnz += (unsigned)nnz;
-
-          // ---- doc bucket: weights + tile scan --------------------------------------------
-          // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any
-          // is consumed, so a multi-tile row pays one memory latency per group, not per tile.
-          const int ntiles = (nnz + 31) >> 5;
-          float carry = 0.0f, P = 0.0f;
-          int jo = 0;
-          for (int t0 = 0; t0 < ntiles; t0 += kGroup) {
-            uint32_t sv[kGroup];
-            int nv[kGroup];
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-              const int j = ((t0 + g) << 5) + lane;
-              sv[g] = 0u;
-              nv[g] = 0;
-              if (j < nnz) {
-                sv[g] = slots[j];
-                const int32_t* cell = nrow + (sv[g] >> 16);
-                nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-              if (t0 + g < ntiles) {
-                const int j = ((t0 + g) << 5) + lane;
-                const bool act = j < nnz;
-                const int topic = (int)(sv[g] >> 16);
-                const bool is_old = act && (topic == o);
-                const unsigned bo = __ballot_sync(kFullMask, is_old);
-                if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
-                const int c = (int)(sv[g] & 0xffffu) - (int)is_old;
-                const int n = max(nv[g] - ((int)is_old & p.exclude_self), 0);
-                const float inv = TABLES_IN_SMEM ? s_tab[topic] : __ldg(p.invden + topic);
-                float a = fmul(fmul(fadd((float)n, beta_f), inv), (float)c);  // c == 0 past nnz
-                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), m1, a);
-                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), m2, a);
-                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), m4, a);
-                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), m8, a);
-                a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), m16, a);
-                P = fadd(carry, a);
-                if (ntiles > 1) pref[j] = P;
-                carry = __shfl_sync(kFullMask, P, 31);
-              }
-            }
-          }
-          const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
-          float delta = TABLES_IN_SMEM ? s_tab[K + o] : __ldg(p.ab + o);
-          delta = p.exclude_self ? delta : 0.0f;
-          float qp = fsub(qw, delta);
-          qp = qp < 0.0f ? 0.0f : qp;
-          const float T = fadd(A, qp);
-          const float x = fmul(u, T);
-
+          doc_nnz += (unsigned)nnz;
           int newt;
-          int jn = -1;  // slot of newt when it is already known to be in the row
-          if (x < A) {
-            jn = nnz - 1;
-            if (ntiles == 1) {
-              const unsigned b = __ballot_sync(kFullMask, (lane < nnz) && (P > x));
-              if (b) jn = __ffs(b) - 1;
-            } else {
-              __syncwarp();
-              for (int tile = 0; tile < ntiles; ++tile) {
-                const int j = (tile << 5) + lane;
-                const bool hit = (j < nnz) && (pref[j] > x);
-                const unsigned b = __ballot_sync(kFullMask, hit);
-                if (b) {
-                  jn = (tile << 5) + __ffs(b) - 1;
-                  break;
-                }
-              }
-            }
-            newt = (int)(slots[jn] >> 16);
-          } else {
-            // ---- prior bucket: skip the own-token mass delta at topic o, then search ----------
-            ++st_prior;
-            const float y = fsub(x, A);
-            const float* prow = p.prior + (size_t)w * p.layout.stride;
-            const float po = __ldg(prow + o);  // level 0 sits at offset 0
-            const float pod = fsub(po, delta);
-            const float s = (y < pod) ? y : fadd(y, delta);
-            int block = 0;
-            for (int lev = p.layout.nlev - 1; lev >= 0; --lev) {
-              const int lo = block << 5;
-              const int nvalid = min(32, p.layout.size[lev] - lo);
-              float v = 0.0f;
-              if (lane < nvalid) v = __ldg(prow + p.layout.off[lev] + lo + lane);
-              const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
-              block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
-            }
-            newt = block;
-          }
-
-          if (MODE == MODE_UPDATE && newt != o) {
-            ++st_moved;
-            // Where does newt live (or go) in the row as it stands, old slot still present?
-            int pos = 0;
-            if (jn < 0) {
-              for (int tile = 0; (tile << 5) < nnz; ++tile) {
-                const int j = (tile << 5) + lane;
-                const bool act = j < nnz;
-                const int topic = act ? (int)(slots[j] >> 16) : 0x7fffffff;
-                const unsigned less = __ballot_sync(kFullMask, topic < newt);
-                const unsigned eq = __ballot_sync(kFullMask, topic == newt);
-                pos += __popc(less);
-                if (eq) jn = (tile << 5) + __ffs(eq) - 1;
-                if (eq || less != kFullMask) break;
-              }
-            }
-            const uint32_t so = slots[jo];
-            const bool del = (so & 0xffffu) == 1u;
-            __syncwarp();
-            if (jn >= 0) {                 // newt already has a slot: bump it
-              if (lane == 0) {
-                slots[jn] += 1u;
-                if (!del) slots[jo] = so - 1u;
-              }
-              if (del) {                   // ... and close the gap the old topic leaves
-                __syncwarp();
-                row_shift_down(slots, jo + 1, nnz, lane);
-                --nnz;
-              }
-            } else if (!del) {             // new slot, old one stays
-              if (lane == 0) slots[jo] = so - 1u;
-              __syncwarp();
-              row_shift_up(slots, pos, nnz, lane);
-              if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
-              ++nnz;
-            } else if (pos <= jo) {        // old slot empties, new one appears below it
-              row_shift_up(slots, pos, jo, lane);
-              if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
-            } else {                       // ... or above it
-              row_shift_down(slots, jo + 1, pos, lane);
-              if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
-            }
-            __syncwarp();
-            // word-topic and topic totals: integer RED atomics (order-independent sums)
-            if (lane == 0 && p.nwk_write != nullptr) {
-              int32_t* wrow = p.nwk_write + (size_t)w * K;
-              atomicAdd(wrow + o, -1);
-              atomicAdd(wrow + newt, 1);
-              atomicAdd(p.nk_delta + o, -1);
-              atomicAdd(p.nk_delta + newt, 1);
-            }
+          switch (nnz >> 5) {  // tiles needed for nnz + 1 slots, minus one
+            case 0: newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 1: newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 2: newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 3: newt = token_step_tiles<4, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            default: newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
           }
           if (lane == t) new_l = newt;
         }
@@ -324,6 +530,11 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
         for (int j = lane; j < nnz; j += 32) p.rows[rp + j] = slots[j];
         if (lane == 0) p.row_nnz[d] = nnz;
       }
+      st_nnz += doc_nnz;
+      st_moved += c.st_moved;
+      st_prior += c.st_prior;
+      c.st_moved = 0;
+      c.st_prior = 0;
       __syncwarp();
     }
   }
