@@ -190,14 +190,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
       const unsigned b = __ballot_sync(kFullMask, in && (P[g] > x));
       if (b) jn = (g << 5) + __ffs(b) - 1;
     }
-    // topic of slot jn: it sits in tile jn >> 5, lane jn & 31
-    uint32_t sj = 0u;
-#pragma unroll
-    for (int g = 0; g < NT; ++g) {
-      const uint32_t v = __shfl_sync(kFullMask, sv[g], jn & 31);
-      if ((jn >> 5) == g) sj = v;
-    }
-    newt = (int)(sj >> 16);
+    newt = (int)(c.slots[jn] >> 16);  // shared memory still holds the row as loaded
   } else {
     ++c.st_prior;
     newt = prior_search(p, lane, w, o, fsub(x, A), delta);
@@ -217,13 +210,8 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
       }
     }
     // the old slot's count decides whether the slot disappears
-    uint32_t so = 0u;
-#pragma unroll
-    for (int g = 0; g < NT; ++g) {
-      const uint32_t v = __shfl_sync(kFullMask, sv[g], jo & 31);
-      if ((jo >> 5) == g) so = v;
-    }
-    const bool del = (so & 0xffffu) == 1u;
+    const bool del = (c.slots[jo] & 0xffffu) == 1u;
+    __syncwarp();  // every lane has read the row before any lane rewrites it
     // destinations [up_lo, up_hi] take the slot below them, [dn_lo, dn_hi] the slot above; ins gets the new slot
     int up_lo = 1, up_hi = 0, dn_lo = 1, dn_hi = 0, ins = -1;
     if (jn >= 0) {
