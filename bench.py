@@ -51,6 +51,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(workload, K, default_K):
+    """DRAM bytes per token of the sampling kernel from the committed ncu capture of this workload
+    (profiles/r01_traffic_<workload>.json: dram__bytes_read.sum + dram__bytes_write.sum over one
+    sweep's class launches). None when no capture exists for this exact workload / K."""
+    if K != default_K:
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", f"r01_traffic_{workload}.json")) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes_per_token"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -321,8 +335,12 @@ def b200_arm(args):
     kernel_ms = cum_sample_ms / max(1, st["cum_sweeps"])
     peak, peak_src = measured_peaks()
     achieved = tokens_rank * a_alg / (kernel_ms / 1e3) / 1e9
+    bpt, traffic_src = measured_traffic(args.workload, K, w["K"])
     roofline = {"bound": "hbm", "kernel": "k_gibbs_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": (bpt * tokens_rank) if bpt is not None else None,  # DRAM bytes per sweep of this rank
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "dram_frac": (bpt * tokens_rank / (kernel_ms / 1e3) / 1e9 / peak) if bpt is not None else None,
                 "alg_bytes_per_token": a_alg, "impl_bytes_per_token": a_impl,
                 "achieved_impl_bytes": tokens_rank * a_impl / (kernel_ms / 1e3) / 1e9,
                 "kernel_ms": kernel_ms, "tokens_per_launch": tokens_rank,
