@@ -246,7 +246,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
   SweepShape sh;
   sh.slot_cap = slot_cap;
   sh.doc_chunk = doc_chunk;
-  const size_t tab = 2 * sizeof(float) * (size_t)c->K;
+  const size_t tab = 3 * sizeof(float) * (size_t)c->K;  // invden, ab, per-CTA n_k delta
   const size_t per_warp = (size_t)kSmemBytesPerSlot * (size_t)slot_cap;
   bool ok = false;
   for (int ts = 1; ts >= 0 && !ok; --ts) {

@@ -86,6 +86,7 @@ struct WarpCtx {
   uint32_t* slots;   // this warp's row in shared memory
   float* pref;       // this warp's prefix scratch (generic path)
   const float* s_tab;  // [invden | ab] in shared memory (TABLES_IN_SMEM)
+  int* s_nkd;          // per-CTA n_k delta accumulator in shared memory (TABLES_IN_SMEM), else nullptr
   unsigned st_moved, st_prior;
 };
 
@@ -116,14 +117,21 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int 
   return block;
 }
 
-__device__ __forceinline__ void count_moves(const SweepParams& p, int lane, int w, int K, int o, int newt) {
-  // word-topic and topic totals: integer RED atomics (order-independent sums)
-  if (lane == 0 && p.nwk_write != nullptr) {
-    int32_t* wrow = p.nwk_write + (size_t)w * K;
+__device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx& c, int w, int o, int newt) {
+  // word-topic totals: integer RED atomics on n_wk (order-independent sums). Topic totals: every
+  // move in the sweep would hit the same K addresses, so they are accumulated per CTA in shared
+  // memory and flushed once at the end of the kernel.
+  if (c.lane == 0 && p.nwk_write != nullptr) {
+    int32_t* wrow = p.nwk_write + (size_t)w * c.K;
     atomicAdd(wrow + o, -1);
     atomicAdd(wrow + newt, 1);
-    atomicAdd(p.nk_delta + o, -1);
-    atomicAdd(p.nk_delta + newt, 1);
+    if (c.s_nkd != nullptr) {
+      atomicAdd(c.s_nkd + o, -1);
+      atomicAdd(c.s_nkd + newt, 1);
+    } else {
+      atomicAdd(p.nk_delta + o, -1);
+      atomicAdd(p.nk_delta + newt, 1);
+    }
   }
 }
 
@@ -266,7 +274,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     }
     nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
     __syncwarp();
-    count_moves(p, lane, w, c.K, o, newt);
+    count_moves(p, c, w, o, newt);
   }
   return newt;
 }
@@ -411,7 +419,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
       if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
     }
     __syncwarp();
-    count_moves(p, lane, w, c.K, o, newt);
+    count_moves(p, c, w, o, newt);
   }
   return newt;
 }
@@ -424,12 +432,15 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
   const int nwarps = blockDim.x >> 5;
   const int K = p.K;
 
+  // shared memory: [invden | ab | n_k delta] (3K words, when TABLES_IN_SMEM), then the warps' rows and prefixes
   float* s_tab = reinterpret_cast<float*>(smem_raw);
-  const int tab_floats = TABLES_IN_SMEM ? 2 * K : 0;
+  const int tab_floats = TABLES_IN_SMEM ? 3 * K : 0;
+  int* s_nkd = TABLES_IN_SMEM ? reinterpret_cast<int*>(s_tab + 2 * K) : nullptr;
   if (TABLES_IN_SMEM) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       s_tab[k] = p.invden[k];
       s_tab[K + k] = p.ab[k];
+      s_nkd[k] = 0;
     }
     __syncthreads();
   }
@@ -447,6 +458,7 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
   c.pref = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)nwarps * p.slot_cap) +
            (size_t)warp * p.slot_cap;
   c.s_tab = s_tab;
+  c.s_nkd = s_nkd;
   c.st_moved = 0;
   c.st_prior = 0;
   uint32_t* slots = c.slots;
@@ -527,6 +539,13 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
     }
   }
 
+  if (TABLES_IN_SMEM && MODE == MODE_UPDATE && p.nwk_write != nullptr) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const int dv = s_nkd[k];
+      if (dv != 0) atomicAdd(p.nk_delta + k, dv);
+    }
+  }
   if (lane == 0) {
     if (st_moved) {
       atomicAdd(p.stats + 0, st_moved);
