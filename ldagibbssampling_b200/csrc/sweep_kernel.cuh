@@ -67,7 +67,10 @@ struct SweepParams {
 #define B200LDA_SWEEP_GROUP 4  // measured on B200: 4 > 3 > 2 > 1 (profiles/r01_tuning.md)
 #endif
 constexpr int kGroup = B200LDA_SWEEP_GROUP;  // generic path: tiles whose gathers are in flight together
-constexpr int kRegTiles = 4;                 // rows of up to 4 tiles (128 slots) take the register path
+#ifndef B200LDA_REG_TILES
+#define B200LDA_REG_TILES 8  // measured: C3 (rows ~150 slots) 1.11 -> 1.41 Gtok/s, C4 unchanged
+#endif
+constexpr int kRegTiles = B200LDA_REG_TILES;  // rows of up to this many tiles take the straight-line register path
 
 // Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot.
 constexpr int kSmemBytesPerSlot = 8;
@@ -512,6 +515,12 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
             case 1: newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
             case 2: newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
             case 3: newt = token_step_tiles<4, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+#if B200LDA_REG_TILES >= 8
+            case 4: newt = token_step_tiles<5, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 5: newt = token_step_tiles<6, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 6: newt = token_step_tiles<7, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+            case 7: newt = token_step_tiles<8, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
+#endif
             default: newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
           }
           if (lane == t) new_l = newt;
