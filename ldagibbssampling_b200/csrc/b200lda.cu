@@ -242,41 +242,51 @@ int sweep_occupancy(int threads, size_t smem, int* occ) {
 
 // Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
 // of slot_cap entries each.
+int occupancy_of(bool ts, int threads, size_t smem, int* out) {
+  int occ[3] = {0, 0, 0};
+  if (ts) {
+    TRY((sweep_occupancy<MODE_UPDATE, true, true>(threads, smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, true>(threads, smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, true>(threads, smem, &occ[2])));
+  } else {
+    TRY((sweep_occupancy<MODE_UPDATE, true, false>(threads, smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, false>(threads, smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, false>(threads, smem, &occ[2])));
+  }
+  *out = std::min(occ[0], std::min(occ[1], occ[2]));
+  return B200LDA_OK;
+}
+
+// Picks, among {tables in shared memory, tables read through L1} x {8, 4, 2, 1 warps per CTA}, the
+// shape with the most resident warps per SM (ties: shared-memory tables, then wider CTAs). At
+// K = 1000 that is smem tables at 4 CTAs x 8 warps; at K = 10 000 the 120 KB of tables would leave
+// one CTA per SM, so they stay in global memory.
 int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepShape* out) {
-  SweepShape sh;
-  sh.slot_cap = slot_cap;
-  sh.doc_chunk = doc_chunk;
   const size_t tab = 3 * sizeof(float) * (size_t)c->K;  // invden, ab, per-CTA n_k delta
   const size_t per_warp = (size_t)kSmemBytesPerSlot * (size_t)slot_cap;
-  bool ok = false;
-  for (int ts = 1; ts >= 0 && !ok; --ts) {
-    for (int wpc = 8; wpc >= 1 && !ok; wpc >>= 1) {
+  SweepShape best;
+  int best_warps = 0;
+  for (int ts = 1; ts >= 0; --ts) {
+    for (int wpc = 8; wpc >= 1; wpc >>= 1) {
       const size_t need = (ts ? tab : 0) + per_warp * wpc;
-      if (need <= kMaxSmemPerCta) {
-        sh.tables_in_smem = ts != 0;
-        sh.warps_per_cta = wpc;
-        sh.smem = need;
-        ok = true;
+      if (need > kMaxSmemPerCta) continue;
+      int occ = 0;
+      TRY(occupancy_of(ts != 0, wpc * 32, need, &occ));
+      if (occ * wpc > best_warps) {
+        best_warps = occ * wpc;
+        best.slot_cap = slot_cap;
+        best.doc_chunk = doc_chunk;
+        best.tables_in_smem = ts != 0;
+        best.warps_per_cta = wpc;
+        best.smem = need;
+        best.ctas = c->sm_count * occ;  // persistent grid: every CTA resident, documents fetched dynamically
       }
     }
   }
-  if (!ok)
+  if (best_warps == 0)
     return fail(B200LDA_ERANGE, "document rows of %d slots do not fit shared memory (K=%d, longest doc=%d)",
                 slot_cap, c->K, longest);
-  const int threads = sh.warps_per_cta * 32;
-  int occ[3] = {0, 0, 0};
-  if (sh.tables_in_smem) {
-    TRY((sweep_occupancy<MODE_UPDATE, true, true>(threads, sh.smem, &occ[0])));
-    TRY((sweep_occupancy<MODE_UPDATE, false, true>(threads, sh.smem, &occ[1])));
-    TRY((sweep_occupancy<MODE_FROZEN, false, true>(threads, sh.smem, &occ[2])));
-  } else {
-    TRY((sweep_occupancy<MODE_UPDATE, true, false>(threads, sh.smem, &occ[0])));
-    TRY((sweep_occupancy<MODE_UPDATE, false, false>(threads, sh.smem, &occ[1])));
-    TRY((sweep_occupancy<MODE_FROZEN, false, false>(threads, sh.smem, &occ[2])));
-  }
-  const int o = std::max(1, std::min(occ[0], std::min(occ[1], occ[2])));
-  sh.ctas = c->sm_count * o;  // persistent grid: every CTA resident, documents fetched dynamically
-  *out = sh;
+  *out = best;
   return B200LDA_OK;
 }
 

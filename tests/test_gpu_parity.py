@@ -25,6 +25,7 @@ CASES = [
     (200, 400, 120.0, 20, 100),
     (150, 300, 200.0, 30, 1000),
     (60, 100, 300.0, 10, 1500),
+    (40, 80, 120.0, 10, 10000),   # tables too large for shared memory: read through L1
 ]
 
 
