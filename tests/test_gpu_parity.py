@@ -194,3 +194,24 @@ def test_corpus_validation_on_device(oracle):
     s.init_assignments(None)
     s.sweep(1)
     assert s.nk().sum() == 65535
+
+
+def test_live_mode_equals_sequential_oracle_when_documents_do_not_interact(oracle):
+    """LIVE mode updates n_wk in place. Across documents that is a race (by design), but documents
+    with disjoint vocabularies never touch the same n_wk rows, so the chain is deterministic and
+    must equal the oracle's sequential rendering of LIVE mode (n_wk moves immediately, tables and
+    n_k from the sweep start) bit for bit."""
+    import ldagibbssampling_b200 as L
+    rng = np.random.default_rng(7)
+    K, words_per_doc = 40, 50
+    lens = [1, 700, 33, 2500, 64, 190]
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = np.concatenate([d * words_per_doc + rng.integers(0, words_per_doc, n) for d, n in enumerate(lens)]).astype(np.int32)
+    V = words_per_doc * len(lens)
+    z0 = oracle.init_z(len(tok), K, 19)
+    s = _sampler(K, V, seed=19, mode=L.MODE_LIVE)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    s.sweep(5)
+    want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 19, 1, 5, live=True)
+    assert np.array_equal(s.assignments(), want)
