@@ -151,6 +151,13 @@ int b200lda_counts_sync_begin(b200lda_ctx* ctx);
 int b200lda_counts_sync_end(b200lda_ctx* ctx);
 int b200lda_synchronize(b200lda_ctx* ctx);
 int b200lda_get_stream(b200lda_ctx* ctx, void** stream);
+/* The same all-reduce(sum) done by the library itself for hosts that keep all n shards in ONE
+ * process (a JVM after setNumThreads(4), the C++ mirror): sums the exchange buffers (or the
+ * hyper-parameter histograms) of the n contexts in place through peer copies. Blocking; the
+ * NCCL path above is the fast one. */
+#define B200LDA_BUFFER_EXCHANGE 0
+#define B200LDA_BUFFER_HYPER 1
+int b200lda_group_allreduce(b200lda_ctx** ctxs, int32_t n, int32_t which);
 
 /* Frozen-snapshot parity mode (north star; no Java counterpart): resample every token once
  * against the current counts WITHOUT moving any count. uniforms == NULL uses Philox with the

@@ -78,6 +78,7 @@ SYMBOLS = [
     ("b200lda_infer", C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P]),
     ("b200lda_synchronize", C.c_int, [_P]),
     ("b200lda_get_stream", C.c_int, [_P, C.POINTER(_P)]),
+    ("b200lda_group_allreduce", C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32]),
     ("b200lda_sample_frozen", C.c_int, [_P, _P, C.c_uint32, _P]),
     ("b200lda_loglik", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("b200lda_loglik_parts", C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -346,6 +347,15 @@ class Sampler:
 
     def reset_stats(self):
         self._check(self._lib.b200lda_reset_stats(self._h))
+
+
+def group_allreduce(samplers, which=0):
+    """In-process all-reduce(sum) of the samplers' exchange (which=0) or hyper (which=1) buffers."""
+    lib = load_library()
+    arr = (C.c_void_p * len(samplers))(*[s._h for s in samplers])
+    rc = lib.b200lda_group_allreduce(arr, len(samplers), which)
+    if rc != OK:
+        raise B200LDAError(rc, lib.b200lda_last_error().decode())
 
 
 def device_count() -> int:

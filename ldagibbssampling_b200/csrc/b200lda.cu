@@ -1393,6 +1393,45 @@ int b200lda_reset_stats(b200lda_ctx* c) {
   return B200LDA_OK;
 }
 
+// In-process all-reduce(sum) of one buffer kind over n contexts (one per GPU, or several per GPU):
+// the functional equivalent of the NCCL all-reduce for hosts that keep all shards in one process
+// (a JVM with setNumThreads(4), the C++ mirror). Gathers onto the first context's device with peer
+// copies, adds there, copies the sum back. Blocking.
+int b200lda_group_allreduce(b200lda_ctx** ctxs, int32_t n, int32_t which) {
+  if (!ctxs || n < 1) return fail(B200LDA_EINVAL, "bad context list");
+  if (which != B200LDA_BUFFER_EXCHANGE && which != B200LDA_BUFFER_HYPER) return fail(B200LDA_EINVAL, "bad buffer kind");
+  std::vector<int32_t*> bufs((size_t)n);
+  size_t count = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    b200lda_ctx* c = ctxs[i];
+    if (!c) return fail(B200LDA_EINVAL, "null context");
+    int32_t* b = which == B200LDA_BUFFER_EXCHANGE ? c->d_exchange : c->d_hyper;
+    const size_t cnt = which == B200LDA_BUFFER_EXCHANGE ? (size_t)c->V * c->K + c->K
+                                                        : ((size_t)c->K + 1) * (size_t)c->hyper_width;
+    if (!b) return fail(B200LDA_ESTATE, "context %d has no such buffer (world_size == 1, or hyper_begin not called)", i);
+    if (i > 0 && cnt != count) return fail(B200LDA_EINVAL, "contexts disagree on the buffer size");
+    count = cnt;
+    bufs[(size_t)i] = b;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (n == 1) return B200LDA_OK;
+  b200lda_ctx* root = ctxs[0];
+  CU(cudaSetDevice(root->cfg.device));
+  TRY(ensure_stage(root, sizeof(int32_t) * count));
+  int32_t* tmp = reinterpret_cast<int32_t*>(root->d_stage);
+  for (int32_t i = 1; i < n; ++i) {
+    CU(cudaMemcpyPeerAsync(tmp, root->cfg.device, bufs[(size_t)i], ctxs[i]->cfg.device, sizeof(int32_t) * count, root->stream));
+    k_add_i32<<<grid_for(root, (int64_t)(count / 4 + 1), 256), 256, 0, root->stream>>>(count, bufs[0], tmp);
+    root->launches += 1;
+  }
+  CU(cudaGetLastError());
+  for (int32_t i = 1; i < n; ++i)
+    CU(cudaMemcpyPeerAsync(bufs[(size_t)i], ctxs[i]->cfg.device, bufs[0], root->cfg.device, sizeof(int32_t) * count, root->stream));
+  CU(cudaStreamSynchronize(root->stream));
+  return B200LDA_OK;
+}
+
 int b200lda_host_alloc(void** out, size_t bytes) {
   if (!out) return fail(B200LDA_EINVAL, "null argument");
   *out = nullptr;

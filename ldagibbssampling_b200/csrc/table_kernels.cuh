@@ -57,6 +57,22 @@ k_prior_rows(int V, int K, const int32_t* __restrict__ nwk, const float* __restr
   }
 }
 
+// acc[i] += add[i]   (in-process reduction of the shards' exchange buffers)
+__global__ void k_add_i32(size_t n, int32_t* __restrict__ acc, const int32_t* __restrict__ add) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n >> 2;
+  int4* a4 = reinterpret_cast<int4*>(acc);
+  const int4* b4 = reinterpret_cast<const int4*>(add);
+  for (size_t i = tid; i < n4; i += stride) {
+    int4 a = a4[i];
+    const int4 b = b4[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    a4[i] = a;
+  }
+  for (size_t i = (n4 << 2) + tid; i < n; i += stride) acc[i] += add[i];
+}
+
 // nk += nk_delta; nk_delta = 0   (single-shard sweep finish)
 __global__ void k_apply_nk(int K, int32_t* __restrict__ nk, int32_t* __restrict__ nk_delta) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -28,28 +28,14 @@ from .partition import partition_by_tokens, shard_corpus
 
 class _LocalReducer:
     """Sums the shards' exchange buffers when every shard lives in this process (several contexts,
-    one per GPU or several per GPU). Device-side adds through torch; no host round trip."""
+    one per GPU or several per GPU): the library's own in-process all-reduce
+    (b200lda_group_allreduce: peer copies + a device add), no host round trip and no NCCL."""
 
     def __init__(self, samplers, which="exchange"):
-        import torch
-        self.torch = torch
-        self.bufs = []
-        for s in samplers:
-            ptr, n = s.exchange_buffer() if which == "exchange" else s.hyper_buffer()
-            dev = torch.device("cuda", s.device)
-            self.bufs.append(torch.as_tensor(_DevBuf(ptr, n), device=dev))
+        self.which = 0 if which == "exchange" else 1
 
     def __call__(self, samplers):
-        torch = self.torch
-        for s in samplers:
-            s.synchronize()
-        total = self.bufs[0]
-        for b in self.bufs[1:]:
-            total += b.to(total.device)
-        for b in self.bufs[1:]:
-            b.copy_(total)
-        for b in self.bufs:
-            torch.cuda.synchronize(b.device)
+        _capi.group_allreduce(samplers, self.which)
 
 
 class _DevBuf:
