@@ -79,6 +79,14 @@ constexpr int kSmemBytesPerSlot = 8;
 #define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
 #endif
 
+// The kernel's dynamic shared memory, addressed by WORD OFFSET everywhere: indexing the extern
+// array keeps every access a plain LDS/STS/ATOMS with an immediate base, whereas pointers carried in
+// a struct decay to generic addresses and cost an address-space conversion per access.
+extern __shared__ __align__(16) unsigned char b200lda_smem_raw[];
+__device__ __forceinline__ uint32_t& smem_u32(int word) { return reinterpret_cast<uint32_t*>(b200lda_smem_raw)[word]; }
+__device__ __forceinline__ float& smem_f32(int word) { return reinterpret_cast<float*>(b200lda_smem_raw)[word]; }
+__device__ __forceinline__ int* smem_i32_ptr(int word) { return reinterpret_cast<int*>(b200lda_smem_raw) + word; }
+
 // Per-warp constants and counters shared by the token-step variants.
 struct WarpCtx {
   int lane;
@@ -86,10 +94,11 @@ struct WarpCtx {
   float beta_f;
   int excl;
   int K;
-  uint32_t* slots;   // this warp's row in shared memory
-  float* pref;       // this warp's prefix scratch (generic path)
-  const float* s_tab;  // [invden | ab] in shared memory (TABLES_IN_SMEM)
-  int* s_nkd;          // per-CTA n_k delta accumulator in shared memory (TABLES_IN_SMEM), else nullptr
+  // word offsets into the kernel's shared memory
+  int slots;   // this warp's row
+  int pref;    // this warp's prefix scratch (generic path)
+  int tab;     // [invden | ab | n_k delta] (TABLES_IN_SMEM): invden at tab, ab at tab + K, deltas at tab + 2K
+  bool nkd_in_smem;
   unsigned st_moved, st_prior;
 };
 
@@ -128,9 +137,9 @@ __device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx&
     int32_t* wrow = p.nwk_write + (size_t)w * c.K;
     atomicAdd(wrow + o, -1);
     atomicAdd(wrow + newt, 1);
-    if (c.s_nkd != nullptr) {
-      atomicAdd(c.s_nkd + o, -1);
-      atomicAdd(c.s_nkd + newt, 1);
+    if (c.nkd_in_smem) {
+      atomicAdd(smem_i32_ptr(c.tab + 2 * c.K + o), -1);
+      atomicAdd(smem_i32_ptr(c.tab + 2 * c.K + newt), 1);
     } else {
       atomicAdd(p.nk_delta + o, -1);
       atomicAdd(p.nk_delta + newt, 1);
@@ -152,7 +161,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
 #pragma unroll
   for (int g = 0; g < NT; ++g) {
     if (g < NT - 1 || lane < last_n) {
-      sv[g] = c.slots[(g << 5) + lane];
+      sv[g] = smem_u32(c.slots + (g << 5) + lane);
       const int32_t* cell = nrow + (sv[g] >> 16);
       nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
     } else {
@@ -170,7 +179,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     if (is_old) myjo = (g << 5) + lane;
     const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
     const int n = max(nv[g] - ((int)is_old & c.excl), 0);
-    const float inv = TS ? c.s_tab[topic] : __ldg(p.invden + topic);
+    const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
     float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
     a = scan_tile(a, c);
     P[g] = fadd(carry, a);
@@ -185,7 +194,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     const float pl = last_n > 0 ? P[NT - 1] : P[NT - 2];
     A = __shfl_sync(kFullMask, pl, (nnz - 1) & 31);
   }
-  float delta = TS ? c.s_tab[c.K + o] : __ldg(p.ab + o);
+  float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
   delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
   qp = qp < 0.0f ? 0.0f : qp;
@@ -201,7 +210,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
       const unsigned b = __ballot_sync(kFullMask, in && (P[g] > x));
       if (b) jn = (g << 5) + __ffs(b) - 1;
     }
-    newt = (int)(c.slots[jn] >> 16);  // shared memory still holds the row as loaded
+    newt = (int)(smem_u32(c.slots + jn) >> 16);  // shared memory still holds the row as loaded
   } else {
     ++c.st_prior;
     newt = prior_search(p, lane, w, o, fsub(x, A), delta);
@@ -221,7 +230,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
       }
     }
     // the old slot's count decides whether the slot disappears
-    const bool del = (c.slots[jo] & 0xffffu) == 1u;
+    const bool del = (smem_u32(c.slots + jo) & 0xffffu) == 1u;
     __syncwarp();  // every lane has read the row before any lane rewrites it
     // destinations [up_lo, up_hi] take the slot below them, [dn_lo, dn_hi] the slot above; ins gets the new slot
     int up_lo = 1, up_hi = 0, dn_lo = 1, dn_hi = 0, ins = -1;
@@ -261,7 +270,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
         below31 = __shfl_sync(kFullMask, ev[g], 31);
         uint32_t nvl = (j >= up_lo && j <= up_hi) ? prev : ev[g];
         if (j == ins) nvl = fresh;
-        if (nvl != sv[g]) c.slots[j] = nvl;
+        if (nvl != sv[g]) smem_u32(c.slots + j) = nvl;
       }
     } else {  // a downward shift, a bare replacement (empty range, ins >= 0) or count edits only
 #pragma unroll
@@ -272,7 +281,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
         if (lane == 31) next = above0;
         uint32_t nvl = (j >= dn_lo && j <= dn_hi) ? next : ev[g];
         if (j == ins) nvl = fresh;
-        if (nvl != sv[g]) c.slots[j] = nvl;
+        if (nvl != sv[g]) smem_u32(c.slots + j) = nvl;
       }
     }
     nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
@@ -310,8 +319,8 @@ template <int MODE, bool LIVE, bool TS>
 __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
                                                float qw) {
   const int lane = c.lane;
-  uint32_t* slots = c.slots;
-  float* pref = c.pref;
+  uint32_t* slots = &smem_u32(c.slots);
+  float* pref = &smem_f32(c.pref);
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
   // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any is
   // consumed, so a wide row pays one memory latency per group, not per tile.
@@ -343,7 +352,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
         if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
         const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
         const int n = max(nv[g] - ((int)is_old & c.excl), 0);
-        const float inv = TS ? c.s_tab[topic] : __ldg(p.invden + topic);
+        const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
         float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);  // cc == 0 past nnz
         a = scan_tile(a, c);
         P = fadd(carry, a);
@@ -353,7 +362,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
     }
   }
   const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
-  float delta = TS ? c.s_tab[c.K + o] : __ldg(p.ab + o);
+  float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
   delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
   qp = qp < 0.0f ? 0.0f : qp;
@@ -429,21 +438,18 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
 
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(const SweepParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int K = p.K;
 
-  // shared memory: [invden | ab | n_k delta] (3K words, when TABLES_IN_SMEM), then the warps' rows and prefixes
-  float* s_tab = reinterpret_cast<float*>(smem_raw);
-  const int tab_floats = TABLES_IN_SMEM ? 3 * K : 0;
-  int* s_nkd = TABLES_IN_SMEM ? reinterpret_cast<int*>(s_tab + 2 * K) : nullptr;
+  // shared memory (words): [invden | ab | n_k delta] (3K, when TABLES_IN_SMEM), the warps' rows, the warps' prefixes
+  const int tab_words = TABLES_IN_SMEM ? 3 * K : 0;
   if (TABLES_IN_SMEM) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      s_tab[k] = p.invden[k];
-      s_tab[K + k] = p.ab[k];
-      s_nkd[k] = 0;
+      smem_f32(k) = p.invden[k];
+      smem_f32(K + k) = p.ab[k];
+      smem_u32(2 * K + k) = 0u;
     }
     __syncthreads();
   }
@@ -457,14 +463,13 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
   c.beta_f = p.beta_f;
   c.excl = p.exclude_self;
   c.K = K;
-  c.slots = reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)warp * p.slot_cap;
-  c.pref = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(s_tab + tab_floats) + (size_t)nwarps * p.slot_cap) +
-           (size_t)warp * p.slot_cap;
-  c.s_tab = s_tab;
-  c.s_nkd = s_nkd;
+  c.tab = 0;
+  c.slots = tab_words + warp * p.slot_cap;
+  c.pref = tab_words + nwarps * p.slot_cap + warp * p.slot_cap;
+  c.nkd_in_smem = TABLES_IN_SMEM;
   c.st_moved = 0;
   c.st_prior = 0;
-  uint32_t* slots = c.slots;
+  uint32_t* slots = &smem_u32(c.slots);
 
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
   const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
   if (TABLES_IN_SMEM && MODE == MODE_UPDATE && p.nwk_write != nullptr) {
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const int dv = s_nkd[k];
+      const int dv = (int)smem_u32(2 * K + k);
       if (dv != 0) atomicAdd(p.nk_delta + k, dv);
     }
   }
