@@ -232,26 +232,37 @@ int push_alpha(b200lda_ctx* c) {
 
 // ---- sampling-kernel launch shapes ----------------------------------------------------------
 
-template <int MODE, bool LIVE, bool TS>
-int sweep_occupancy(int threads, size_t smem, int* occ) {
-  CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, LIVE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int MODE, bool LIVE, bool TS, int RC>
+int sweep_occupancy_rc(int threads, size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(k_gibbs_sweep<MODE, LIVE, TS, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)kMaxSmemPerCta));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gibbs_sweep<MODE, LIVE, TS>, threads, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gibbs_sweep<MODE, LIVE, TS, RC>, threads, smem));
   return B200LDA_OK;
 }
+template <int MODE, bool LIVE, bool TS>
+int sweep_occupancy(int rc, int threads, size_t smem, int* occ) {
+  switch (rc) {
+    case 0: return sweep_occupancy_rc<MODE, LIVE, TS, 0>(threads, smem, occ);
+    case 1: return sweep_occupancy_rc<MODE, LIVE, TS, 1>(threads, smem, occ);
+    default: return sweep_occupancy_rc<MODE, LIVE, TS, 2>(threads, smem, occ);
+  }
+}
+
+// which kernel instance serves rows of this capacity (sweep_kernel.cuh: ROWCLASS)
+int rowclass_for(int slot_cap) { return slot_cap <= 64 ? 0 : slot_cap <= 128 ? 1 : 2; }
 
 // Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
 // of slot_cap entries each.
-int occupancy_of(bool ts, int threads, size_t smem, int* out) {
+int occupancy_of(bool ts, int rc, int threads, size_t smem, int* out) {
   int occ[3] = {0, 0, 0};
   if (ts) {
-    TRY((sweep_occupancy<MODE_UPDATE, true, true>(threads, smem, &occ[0])));
-    TRY((sweep_occupancy<MODE_UPDATE, false, true>(threads, smem, &occ[1])));
-    TRY((sweep_occupancy<MODE_FROZEN, false, true>(threads, smem, &occ[2])));
+    TRY((sweep_occupancy<MODE_UPDATE, true, true>(rc, threads, smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, true>(rc, threads, smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, true>(rc, threads, smem, &occ[2])));
   } else {
-    TRY((sweep_occupancy<MODE_UPDATE, true, false>(threads, smem, &occ[0])));
-    TRY((sweep_occupancy<MODE_UPDATE, false, false>(threads, smem, &occ[1])));
-    TRY((sweep_occupancy<MODE_FROZEN, false, false>(threads, smem, &occ[2])));
+    TRY((sweep_occupancy<MODE_UPDATE, true, false>(rc, threads, smem, &occ[0])));
+    TRY((sweep_occupancy<MODE_UPDATE, false, false>(rc, threads, smem, &occ[1])));
+    TRY((sweep_occupancy<MODE_FROZEN, false, false>(rc, threads, smem, &occ[2])));
   }
   *out = std::min(occ[0], std::min(occ[1], occ[2]));
   return B200LDA_OK;
@@ -271,7 +282,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
       const size_t need = (ts ? tab : 0) + per_warp * wpc;
       if (need > kMaxSmemPerCta) continue;
       int occ = 0;
-      TRY(occupancy_of(ts != 0, wpc * 32, need, &occ));
+      TRY(occupancy_of(ts != 0, rowclass_for(slot_cap), wpc * 32, need, &occ));
       if (occ * wpc > best_warps) {
         best_warps = occ * wpc;
         best.slot_cap = slot_cap;
@@ -542,10 +553,17 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
   const int ctas = (int)std::max<int64_t>(
       1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
-  if (sh.tables_in_smem)
-    k_gibbs_sweep<MODE, LIVE, true><<<ctas, sh.warps_per_cta * 32, sh.smem, stream>>>(p);
-  else
-    k_gibbs_sweep<MODE, LIVE, false><<<ctas, sh.warps_per_cta * 32, sh.smem, stream>>>(p);
+  const int threads = sh.warps_per_cta * 32;
+#define B200LDA_LAUNCH(TS, RC) k_gibbs_sweep<MODE, LIVE, TS, RC><<<ctas, threads, sh.smem, stream>>>(p)
+  switch (rowclass_for(sh.slot_cap) * 2 + (sh.tables_in_smem ? 1 : 0)) {
+    case 0: B200LDA_LAUNCH(false, 0); break;
+    case 1: B200LDA_LAUNCH(true, 0); break;
+    case 2: B200LDA_LAUNCH(false, 1); break;
+    case 3: B200LDA_LAUNCH(true, 1); break;
+    case 4: B200LDA_LAUNCH(false, 2); break;
+    default: B200LDA_LAUNCH(true, 2); break;
+  }
+#undef B200LDA_LAUNCH
   c->launches += 1;
   CU(cudaGetLastError());
   return B200LDA_OK;

@@ -78,6 +78,12 @@ constexpr int kSmemBytesPerSlot = 8;
 #ifndef B200LDA_SWEEP_MIN_CTAS
 #define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
 #endif
+#ifndef B200LDA_ROWCLASS0_MIN_CTAS
+#define B200LDA_ROWCLASS0_MIN_CTAS 4
+#endif
+#ifndef B200LDA_ROWCLASS1_MIN_CTAS
+#define B200LDA_ROWCLASS1_MIN_CTAS 4
+#endif
 
 // The kernel's dynamic shared memory, addressed by WORD OFFSET everywhere: indexing the extern
 // array keeps every access a plain LDS/STS/ATOMS with an immediate base, whereas pointers carried in
@@ -436,8 +442,18 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
   return newt;
 }
 
-template <int MODE, bool LIVE, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(const SweepParams p) {
+// ROWCLASS selects which token-step variants a kernel instance carries, so that the register
+// allocation (one per kernel) of the narrow-row classes is not dictated by the 8-tile variant:
+//   0: rows <= 64 slots  (NT <= 3)     1: rows <= 128 slots (NT <= 5)     2: any row (NT <= 8 + loop form)
+constexpr int kRowClasses = 3;
+__host__ __device__ constexpr int rowclass_max_tiles(int rc) { return rc == 0 ? 3 : rc == 1 ? 5 : 8; }
+__host__ __device__ constexpr int rowclass_min_ctas(int rc) {
+  return rc == 0 ? B200LDA_ROWCLASS0_MIN_CTAS : rc == 1 ? B200LDA_ROWCLASS1_MIN_CTAS : B200LDA_SWEEP_MIN_CTAS;
+}
+
+template <int MODE, bool LIVE, bool TABLES_IN_SMEM, int ROWCLASS>
+__global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_sweep(const SweepParams p) {
+  constexpr int MAXNT = rowclass_max_tiles(ROWCLASS);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -515,19 +531,16 @@ __global__ void __launch_bounds__(256, B200LDA_SWEEP_MIN_CTAS) k_gibbs_sweep(con
           const float qw = __shfl_sync(kFullMask, q_l, t);
           doc_nnz += (unsigned)nnz;
           int newt;
-          switch (nnz >> 5) {  // tiles needed for nnz + 1 slots, minus one
-            case 0: newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 1: newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 2: newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 3: newt = token_step_tiles<4, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-#if B200LDA_REG_TILES >= 8
-            case 4: newt = token_step_tiles<5, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 5: newt = token_step_tiles<6, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 6: newt = token_step_tiles<7, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-            case 7: newt = token_step_tiles<8, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-#endif
-            default: newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw); break;
-          }
+          const int tile_case = nnz >> 5;  // tiles needed for nnz + 1 slots, minus one (uniform across the warp)
+          if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
+          else newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw);
           if (lane == t) new_l = newt;
         }
 
