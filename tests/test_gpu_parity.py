@@ -215,3 +215,28 @@ def test_live_mode_equals_sequential_oracle_when_documents_do_not_interact(oracl
     s.sweep(5)
     want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 19, 1, 5, live=True)
     assert np.array_equal(s.assignments(), want)
+
+
+@pytest.mark.parametrize("K,V,lens", [
+    (1, 5, [3, 40, 1]),                 # a single topic: every draw must return topic 0
+    (2, 1, [100, 7]),                   # a single word type
+    (3, 6, [500]),                      # one document much longer than K (row capacity = K, always full)
+    (33, 9, [64, 65, 31, 32, 33, 200]), # K just past one tile: rows cross the 32-slot boundary both ways
+    (64, 50, [64, 129, 300]),           # rows that fill their class capacity exactly
+])
+def test_edge_shapes_match_oracle(oracle, K, V, lens):
+    rng = np.random.default_rng(K * 1000 + V)
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z0 = oracle.init_z(len(tok), K, 4)
+    s = _sampler(K, V, seed=4)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    assert np.array_equal(s.sample_frozen(None, 2), oracle.spec_frozen(dp, tok, z0, V, K, ALPHA, BETA, 4, 2))
+    s.sweep(6)
+    want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 4, 1, 6)
+    assert np.array_equal(s.assignments(), want)
+    nwk, nk = oracle.count(dp, tok, want, V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    ll = oracle.loglik(dp, tok, want, V, K, ALPHA, BETA)
+    assert abs(s.loglik() - ll) <= 1e-9 * abs(ll)
