@@ -197,18 +197,6 @@ __global__ void k_word_scatter(int64_t N, const int32_t* __restrict__ tok_word, 
   }
 }
 
-// n_wk from the word -> token order: consecutive threads touch the same / neighbouring n_wk rows,
-// so the integer atomics stay in L2 and a frequent word is spread over many warps.
-__global__ void __launch_bounds__(256)
-k_count_sorted(int64_t N, int K, const int64_t* __restrict__ wtok, const int32_t* __restrict__ tok_word,
-               const uint16_t* __restrict__ z, int32_t* __restrict__ nwk) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    const int64_t t = wtok[i];
-    atomicAdd(nwk + (size_t)tok_word[t] * K + z[t], 1);
-  }
-}
-
 // n_wk straight from the doc -> token order (no word order needed): streaming reads, random REDs.
 __global__ void __launch_bounds__(256)
 k_count_direct(int64_t N, int K, const int32_t* __restrict__ tok_word, const uint16_t* __restrict__ z,
