@@ -17,13 +17,31 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 
+// One Kogge-Stone step: v += (value of lane l-d) for lanes l >= d. shfl.sync.up returns, besides the
+// value, a predicate telling whether the source lane was in range, so the step is SHFL + a
+// predicated add.rn.f32 (individually rounded, never contracted): no lane compare, no select.
+__device__ __forceinline__ float scan_step(float v, int d) {
+  float out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .f32 y;\n\t"
+      "shfl.sync.up.b32 y|p, %1, %2, 0x0, 0xffffffff;\n\t"
+      "mov.f32 %0, %1;\n\t"
+      "@p add.rn.f32 %0, %1, y;\n\t"
+      "}"
+      : "=f"(out)
+      : "f"(v), "r"(d));
+  return out;
+}
+
 // Inclusive Kogge-Stone scan over the 32 lanes of a warp (lane l adds lane l-d for d=1,2,4,8,16).
-__device__ __forceinline__ float warp_scan_inclusive(float v, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const float y = __shfl_up_sync(kFullMask, v, d);
-    if (lane >= d) v = fadd(v, y);
-  }
+__device__ __forceinline__ float warp_scan_inclusive(float v, int /*lane*/) {
+  v = scan_step(v, 1);
+  v = scan_step(v, 2);
+  v = scan_step(v, 4);
+  v = scan_step(v, 8);
+  v = scan_step(v, 16);
   return v;
 }
 

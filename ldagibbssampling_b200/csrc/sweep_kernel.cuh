@@ -96,7 +96,6 @@ __device__ __forceinline__ int* smem_i32_ptr(int word) { return reinterpret_cast
 // Per-warp constants and counters shared by the token-step variants.
 struct WarpCtx {
   int lane;
-  float m1, m2, m4, m8, m16;  // Kogge-Stone lane masks: v = y*m + v is "if (lane >= d) v += y" in one FFMA
   float beta_f;
   int excl;
   int K;
@@ -108,14 +107,7 @@ struct WarpCtx {
   unsigned st_moved, st_prior;
 };
 
-__device__ __forceinline__ float scan_tile(float a, const WarpCtx& c) {
-  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 1), c.m1, a);
-  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 2), c.m2, a);
-  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 4), c.m4, a);
-  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 8), c.m8, a);
-  a = __fmaf_rn(__shfl_up_sync(kFullMask, a, 16), c.m16, a);
-  return a;
-}
+__device__ __forceinline__ float scan_tile(float a, const WarpCtx&) { return warp_scan_inclusive(a, 0); }
 
 // Prior bucket: skip the own-token mass delta at topic o, then the fan-out-32 search.
 __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int w, int o, float y, float delta) {
@@ -471,11 +463,6 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   }
   WarpCtx c;
   c.lane = lane;
-  c.m1 = lane >= 1 ? 1.0f : 0.0f;
-  c.m2 = lane >= 2 ? 1.0f : 0.0f;
-  c.m4 = lane >= 4 ? 1.0f : 0.0f;
-  c.m8 = lane >= 8 ? 1.0f : 0.0f;
-  c.m16 = lane >= 16 ? 1.0f : 0.0f;
   c.beta_f = p.beta_f;
   c.excl = p.exclude_self;
   c.K = K;
