@@ -104,6 +104,7 @@ struct WarpCtx {
   int pref;    // this warp's prefix scratch (generic path)
   int tab;     // [invden | ab | n_k delta] (TABLES_IN_SMEM): invden at tab, ab at tab + K, deltas at tab + 2K
   bool nkd_in_smem;
+  int top_lane;  // offset of this lane's entry of the top search level inside a word's prior block, -1: none
   unsigned st_moved, st_prior;
 };
 
@@ -114,10 +115,9 @@ __device__ __forceinline__ float scan_tile(float a, const WarpCtx&) { return war
 // per 32-token batch (one lane per token) and, for narrow rows, this lane's entry of the top search
 // level is requested at the start of the token step, before the bucket is known. A draw that lands
 // in the prior bucket then pays one dependent memory access per remaining level only.
-__device__ __forceinline__ float prior_top_entry(const SweepParams& p, int lane, int w) {
-  const int top = p.layout.nlev - 1;
+__device__ __forceinline__ float prior_top_entry(const SweepParams& p, const WarpCtx& c, int w) {
   const float* prow = p.prior + (size_t)w * p.layout.stride;
-  return (lane < p.layout.size[top]) ? __ldg(prow + p.layout.off[top] + lane) : 0.0f;
+  return (c.top_lane >= 0) ? __ldg(prow + c.top_lane) : 0.0f;
 }
 __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int w, float po, float y, float delta,
                                             float vtop) {
@@ -168,7 +168,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
   const int last_n = nnz - 32 * (NT - 1);  // active lanes of the last tile, 0..31
   constexpr bool kTopEarly = NT <= 3;  // wider rows have no register to spare for it (measured: C3 -8 %)
   float vtop = 0.0f;
-  if (kTopEarly) vtop = prior_top_entry(p, lane, w);
+  if (kTopEarly) vtop = prior_top_entry(p, c, w);
   uint32_t sv[NT];
   int nv[NT];
 #pragma unroll
@@ -226,7 +226,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     newt = (int)(smem_u32(c.slots + jn) >> 16);  // shared memory still holds the row as loaded
   } else {
     ++c.st_prior;
-    if (!kTopEarly) vtop = prior_top_entry(p, lane, w);
+    if (!kTopEarly) vtop = prior_top_entry(p, c, w);
     newt = prior_search(p, lane, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, vtop);
   }
 
@@ -399,7 +399,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
     newt = (int)(slots[jn] >> 16);
   } else {
     ++c.st_prior;
-    newt = prior_search(p, lane, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, lane, w));
+    newt = prior_search(p, lane, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, c, w));
   }
 
   if (MODE == MODE_UPDATE && newt != o) {
@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   c.slots = tab_words + warp * p.slot_cap;
   c.pref = tab_words + nwarps * p.slot_cap + warp * p.slot_cap;
   c.nkd_in_smem = TABLES_IN_SMEM;
+  c.top_lane = (lane < p.layout.size[p.layout.nlev - 1]) ? p.layout.off[p.layout.nlev - 1] + lane : -1;
   c.st_moved = 0;
   c.st_prior = 0;
   uint32_t* slots = &smem_u32(c.slots);
