@@ -246,57 +246,43 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     // the old slot's count decides whether the slot disappears
     const bool del = (smem_u32(c.slots + jo) & 0xffffu) == 1u;
     __syncwarp();  // every lane has read the row before any lane rewrites it
-    // destinations [up_lo, up_hi] take the slot below them, [dn_lo, dn_hi] the slot above; ins gets the new slot
-    int up_lo = 1, up_hi = 0, dn_lo = 1, dn_hi = 0, ins = -1;
-    if (jn >= 0) {
-      if (del) {
-        dn_lo = jo;
-        dn_hi = nnz - 2;
+    // The edit happens in shared memory: two single-lane count updates, then (only when a slot
+    // appears or disappears) a one-slot shift of [lo, lo + width] read as a whole before it is
+    // written back. Measured against editing the register copy with shuffles: fewer instructions
+    // per tile (range test + LDS + STS) and no second copy of the row in registers.
+    if (lane == 0 && jn >= 0) smem_u32(c.slots + jn) += 1u;
+    if (lane == 1 && !del) smem_u32(c.slots + jo) -= 1u;
+    if (jn < 0 || del) {
+      // destinations [lo, lo + width] take the slot at +off; ins gets the new slot (outside the range)
+      int lo = 0x7fffffff, width = 0, off = 0, ins = -1;
+      if (jn >= 0) {             // old slot empties, newt has one already: close the gap
+        lo = jo; width = nnz - 2 - jo; off = 1;
+      } else if (!del) {         // new slot, old one stays: open a gap at pos
+        lo = pos + 1; width = nnz - pos - 1; off = -1; ins = pos;
+      } else if (pos <= jo) {    // old slot empties, new one appears at or below it
+        lo = pos + 1; width = jo - pos - 1; off = -1; ins = pos;
+      } else {                   // ... or above it
+        lo = jo; width = pos - 2 - jo; off = 1; ins = pos - 1;
       }
-    } else if (!del) {
-      up_lo = pos + 1;
-      up_hi = nnz;
-      ins = pos;
-    } else if (pos <= jo) {
-      up_lo = pos + 1;
-      up_hi = jo;
-      ins = pos;
-    } else {
-      dn_lo = jo;
-      dn_hi = pos - 2;
-      ins = pos - 1;
-    }
-    const uint32_t fresh = ((uint32_t)newt << 16) | 1u;
-    // count edits first (they travel with the slots when those shift); sv keeps what shared memory holds
-    uint32_t ev[NT];
-#pragma unroll
-    for (int g = 0; g < NT; ++g) {
-      const int j = (g << 5) + lane;
-      ev[g] = sv[g] + (j == jn ? 1u : 0u) - ((j == jo && !del) ? 1u : 0u);
-    }
-    if (up_hi >= up_lo) {
-      uint32_t below31 = 0u;  // lane 31 of the tile below
+      if (width < 0) {  // empty range: a bare replacement of the old slot
+        lo = 0x7fffffff;
+        width = 0;
+      }
+      __syncwarp();  // count updates visible
+      uint32_t mv[NT];
 #pragma unroll
       for (int g = 0; g < NT; ++g) {
         const int j = (g << 5) + lane;
-        uint32_t prev = __shfl_up_sync(kFullMask, ev[g], 1);
-        if (lane == 0) prev = below31;
-        below31 = __shfl_sync(kFullMask, ev[g], 31);
-        uint32_t nvl = (j >= up_lo && j <= up_hi) ? prev : ev[g];
-        if (j == ins) nvl = fresh;
-        if (nvl != sv[g]) smem_u32(c.slots + j) = nvl;
+        mv[g] = 0u;
+        if ((unsigned)(j - lo) <= (unsigned)width) mv[g] = smem_u32(c.slots + j + off);
       }
-    } else {  // a downward shift, a bare replacement (empty range, ins >= 0) or count edits only
+      __syncwarp();  // whole range read before any of it is overwritten
 #pragma unroll
-      for (int g = NT - 1; g >= 0; --g) {
+      for (int g = 0; g < NT; ++g) {
         const int j = (g << 5) + lane;
-        uint32_t next = __shfl_down_sync(kFullMask, ev[g], 1);
-        const uint32_t above0 = (g + 1 < NT) ? __shfl_sync(kFullMask, ev[g + 1 < NT ? g + 1 : g], 0) : 0u;
-        if (lane == 31) next = above0;
-        uint32_t nvl = (j >= dn_lo && j <= dn_hi) ? next : ev[g];
-        if (j == ins) nvl = fresh;
-        if (nvl != sv[g]) smem_u32(c.slots + j) = nvl;
+        if ((unsigned)(j - lo) <= (unsigned)width) smem_u32(c.slots + j) = mv[g];
       }
+      if (lane == 0 && ins >= 0) smem_u32(c.slots + ins) = ((uint32_t)newt << 16) | 1u;
     }
     nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
     __syncwarp();
