@@ -139,20 +139,24 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int 
   return block;
 }
 
-__device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx& c, int w, int o, int newt) {
-  // word-topic totals: integer RED atomics on n_wk (order-independent sums). Topic totals: every
-  // move in the sweep would hit the same K addresses, so they are accumulated per CTA in shared
-  // memory and flushed once at the end of the kernel.
-  if (c.lane == 0 && p.nwk_write != nullptr) {
-    int32_t* wrow = p.nwk_write + (size_t)w * c.K;
-    atomicAdd(wrow + o, -1);
-    atomicAdd(wrow + newt, 1);
+// Count moves of one token: -1 at the old topic from lane 0, +1 at the new topic from lane 1.
+// Word-topic totals: integer RED atomics on the word's n_wk row (order-independent sums). Topic
+// totals: every move in the sweep would hit the same K addresses, so they are accumulated per CTA
+// in shared memory and flushed once at the end of the kernel.
+template <bool LIVE>
+__device__ __forceinline__ int32_t* write_row(const SweepParams& p, const int32_t* nrow, int w, int K) {
+  if (LIVE) return const_cast<int32_t*>(nrow);  // in place: nwk_write == nwk_read
+  return p.nwk_write ? p.nwk_write + (size_t)w * K : nullptr;
+}
+__device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx& c, int32_t* wrow, int o, int newt) {
+  if (c.lane < 2 && wrow != nullptr) {
+    const int topic = c.lane == 0 ? o : newt;
+    const int val = c.lane == 0 ? -1 : 1;
+    atomicAdd(wrow + topic, val);
     if (c.nkd_in_smem) {
-      atomicAdd(smem_i32_ptr(c.tab + 2 * c.K + o), -1);
-      atomicAdd(smem_i32_ptr(c.tab + 2 * c.K + newt), 1);
+      atomicAdd(smem_i32_ptr(c.tab + 2 * c.K + topic), val);
     } else {
-      atomicAdd(p.nk_delta + o, -1);
-      atomicAdd(p.nk_delta + newt, 1);
+      atomicAdd(p.nk_delta + topic, val);
     }
   }
 }
@@ -286,7 +290,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     }
     nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
     __syncwarp();
-    count_moves(p, c, w, o, newt);
+    count_moves(p, c, write_row<LIVE>(p, nrow, w, c.K), o, newt);
   }
   return newt;
 }
@@ -431,7 +435,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
       if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
     }
     __syncwarp();
-    count_moves(p, c, w, o, newt);
+    count_moves(p, c, write_row<LIVE>(p, nrow, w, c.K), o, newt);
   }
   return newt;
 }
