@@ -274,7 +274,7 @@ int occupancy_of(bool ts, int rc, int threads, size_t smem, int* out) {
 // one CTA per SM, so they stay in global memory.
 int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepShape* out) {
   const size_t tab = 3 * sizeof(float) * (size_t)c->K;  // invden, ab, per-CTA n_k delta
-  const size_t per_warp = (size_t)kSmemBytesPerSlot * (size_t)slot_cap;
+  const size_t per_warp = sweep_smem_per_warp(slot_cap);
   SweepShape best;
   int best_warps = 0;
   for (int ts = 1; ts >= 0; --ts) {

@@ -9,15 +9,19 @@
 //     forms  n_dk (n_wk + beta) / (n_k + V beta)  and the warp scans it (shuffle prefix sum);
 //   * prior bucket: alpha_k (n_wk + beta) / (n_k + V beta) is word-only, so its mass and prefix
 //     table are built once per sweep per word (table_kernels.cuh); a draw that lands there is
-//     resolved by a fan-out-32 search = one coalesced 128-byte line per level;
+//     resolved by a fan-out-32 search = one coalesced 128-byte line per level, and the loads that
+//     depend only on the token (P_w[o], the top level) are requested before the bucket is known;
 //   * randomness: Philox keyed by (seed; global token, sweep), 32 tokens per warp batch, one
 //     lane each, so the RNG costs ~2 instructions per token;
-//   * count moves: the row edit happens in registers (one shuffle per tile) for rows of up to
-//     kRegTiles tiles, integer RED atomics carry the n_wk / n_k moves.
-// The kernel is instruction-issue bound (profiles/r01_sweep_v3_ncu_summary.txt), so the token step
-// is specialised on the number of 32-slot tiles of the row: token_step_tiles<NT> is straight-line
-// code (full tiles unpredicated, prefixes in registers, no inner loops); token_step_generic keeps
-// the loop form for rows wider than kRegTiles tiles.
+//   * count moves: the row edit happens in shared memory (two count updates, a one-slot shift only
+//     when a topic enters or leaves the document), integer RED atomics carry the n_wk / n_k moves.
+// The kernel is limited by instruction issue (72-77 % of issue slots) with L1TEX second
+// (profiles/r01_sweep_v7_ncu_summary.txt, profiles/r01_tuning.md), so the token step is specialised
+// on the number of 32-slot tiles of the row: token_step_tiles<NT> is straight-line code (rows
+// zero-padded to whole tiles so nothing is predicated per lane, prefixes in registers, no inner
+// loops); token_step_generic keeps the loop form for rows wider than kRegTiles tiles. Slots stay in
+// tile order (lane = slot mod 32) on purpose: 32 consecutive sorted topics per gather instruction
+// touch ~13 of the word row's 32 lines, a lane-blocked order touches 32 and is L1TEX-bound.
 // Documents are visited through doc_order (longest first); the host launches the kernel once per
 // row-width class so that per-warp shared memory follows the row width.
 // MODE_UPDATE serves LIVE (LIVE=true: n_wk read through L2 and written in place) and DEFERRED
@@ -72,8 +76,13 @@ constexpr int kGroup = B200LDA_SWEEP_GROUP;  // generic path: tiles whose gather
 #endif
 constexpr int kRegTiles = B200LDA_REG_TILES;  // rows of up to this many tiles take the straight-line register path
 
-// Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot.
+// Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot, plus
+// kRowPad zeroed spare slots behind the row (the register path reads whole tiles).
 constexpr int kSmemBytesPerSlot = 8;
+constexpr int kRowPad = 32;
+__host__ __device__ constexpr size_t sweep_smem_per_warp(int slot_cap) {
+  return (size_t)kSmemBytesPerSlot * (size_t)slot_cap + sizeof(uint32_t) * kRowPad;
+}
 
 #ifndef B200LDA_SWEEP_MIN_CTAS
 #define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
@@ -162,8 +171,10 @@ __device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx&
 }
 
 // ---- register path: rows that fit NT tiles with room for one more slot (nnz + 1 <= 32 NT) -------
-// Tiles 0 .. NT-2 are full, so only the last tile is predicated; prefixes stay in registers; the
-// row edit is a one-slot shift done with shuffles on the row registers, then stored back.
+// The warp's row in shared memory is ZERO-PADDED past nnz up to 32 NT slots (kRowPad spare slots
+// behind slot_cap): a padded slot reads topic 0 / count 0, weighs exactly +0 and can never be the
+// old topic's slot, so loads, weights and the bucket search carry no per-lane validity predicate.
+// Prefixes stay in registers; the row edit happens in shared memory.
 template <int NT, int MODE, bool LIVE, bool TS>
 __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
                                                 float qw, float po_l, int t) {
@@ -177,22 +188,19 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
   int nv[NT];
 #pragma unroll
   for (int g = 0; g < NT; ++g) {
-    if (g < NT - 1 || lane < last_n) {
-      sv[g] = smem_u32(c.slots + (g << 5) + lane);
-      const int32_t* cell = nrow + (sv[g] >> 16);
-      nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
-    } else {
-      sv[g] = 0u;  // count 0 => weight exactly 0
-      nv[g] = 0;
-    }
+    sv[g] = smem_u32(c.slots + (g << 5) + lane);
+    const int32_t* cell = nrow + (sv[g] >> 16);  // padded slots read n_wk[w, 0]: harmless, weight is 0
+    nv[g] = LIVE ? __ldcg(cell) : __ldg(cell);
   }
+  // a live slot of topic o reads (o << 16) + count with 1 <= count <= 0xffff
+  const uint32_t okey = ((uint32_t)o << 16) + 1u;
   float P[NT];
   float carry = 0.0f;
   int myjo = -1;
 #pragma unroll
   for (int g = 0; g < NT; ++g) {
     const int topic = (int)(sv[g] >> 16);
-    const bool is_old = (topic == o) && (g < NT - 1 || lane < last_n);
+    const bool is_old = (sv[g] - okey) < 0xffffu;
     if (is_old) myjo = (g << 5) + lane;
     const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
     const int n = max(nv[g] - ((int)is_old & c.excl), 0);
@@ -223,8 +231,8 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     jn = nnz - 1;
 #pragma unroll
     for (int g = NT - 1; g >= 0; --g) {  // descending, so the lowest tile with a hit wins
-      const bool in = (g < NT - 1) || (lane < last_n);
-      const unsigned b = __ballot_sync(kFullMask, in && (P[g] > x));
+      // slot nnz-1 is a hit (x < A), so a padded slot, which sits above it, never comes first
+      const unsigned b = __ballot_sync(kFullMask, P[g] > x);
       if (b) jn = (g << 5) + __ffs(b) - 1;
     }
     newt = (int)(smem_u32(c.slots + jn) >> 16);  // shared memory still holds the row as loaded
@@ -238,14 +246,16 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     ++c.st_moved;
     int pos = 0;  // #slots with topic < newt (old slot still present); only needed when newt is new to the row
     if (jn < 0) {
+      // packed compares that a padded slot (0) fails: live slot of topic < newt, live slot of topic == newt
+      const uint32_t nkey = (uint32_t)newt << 16;
+      int less = 0, eqj = -1;
 #pragma unroll
       for (int g = 0; g < NT; ++g) {
-        const bool in = (g < NT - 1) || (lane < last_n);
-        const int topic = in ? (int)(sv[g] >> 16) : 0x7fffffff;
-        pos += __popc(__ballot_sync(kFullMask, topic < newt));
-        const unsigned eq = __ballot_sync(kFullMask, topic == newt);
-        if (eq) jn = (g << 5) + __ffs(eq) - 1;
+        less += ((sv[g] - 1u) < nkey) ? 1 : 0;
+        if ((sv[g] - nkey - 1u) < 0xffffu) eqj = (g << 5) + lane;
       }
+      pos = __reduce_add_sync(kFullMask, less);
+      jn = __reduce_max_sync(kFullMask, eqj);
     }
     // the old slot's count decides whether the slot disappears
     const bool del = (smem_u32(c.slots + jo) & 0xffffu) == 1u;
@@ -259,8 +269,8 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     if (jn < 0 || del) {
       // destinations [lo, lo + width] take the slot at +off; ins gets the new slot (outside the range)
       int lo = 0x7fffffff, width = 0, off = 0, ins = -1;
-      if (jn >= 0) {             // old slot empties, newt has one already: close the gap
-        lo = jo; width = nnz - 2 - jo; off = 1;
+      if (jn >= 0) {             // old slot empties, newt has one already: close the gap (slot nnz-1 takes the padding's 0)
+        lo = jo; width = nnz - 1 - jo; off = 1;
       } else if (!del) {         // new slot, old one stays: open a gap at pos
         lo = pos + 1; width = nnz - pos - 1; off = -1; ins = pos;
       } else if (pos <= jo) {    // old slot empties, new one appears at or below it
@@ -420,6 +430,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
         __syncwarp();
         row_shift_down(slots, jo + 1, nnz, lane);
         --nnz;
+        if (lane == 0) slots[nnz] = 0u;  // keep the zero padding behind the row
       }
     } else if (!del) {             // new slot, old one stays
       if (lane == 0) slots[jo] = so - 1u;
@@ -473,8 +484,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   c.excl = p.exclude_self;
   c.K = K;
   c.tab = 0;
-  c.slots = tab_words + warp * p.slot_cap;
-  c.pref = tab_words + nwarps * p.slot_cap + warp * p.slot_cap;
+  const int row_words = p.slot_cap + kRowPad;
+  c.slots = tab_words + warp * row_words;
+  c.pref = tab_words + nwarps * row_words + warp * p.slot_cap;
   c.nkd_in_smem = TABLES_IN_SMEM;
   c.top_lane = (lane < p.layout.size[p.layout.nlev - 1]) ? p.layout.off[p.layout.nlev - 1] + lane : -1;
   c.st_moved = 0;
@@ -497,7 +509,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
       if (te == tb) continue;
       const int64_t rp = p.row_ptr[d];
       int nnz = p.row_nnz[d];
-      for (int j = lane; j < nnz; j += 32) slots[j] = p.rows[rp + j];
+      for (int j = lane; j < row_words; j += 32) slots[j] = j < nnz ? p.rows[rp + j] : 0u;  // zero-padded
       __syncwarp();
       unsigned doc_nnz = 0;
 
