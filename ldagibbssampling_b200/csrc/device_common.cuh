@@ -2,9 +2,10 @@
 //
 // Arithmetic contract ("sampling spec"): every fp32 operation that feeds a sampling
 // decision goes through the __f*_rn intrinsics below, so nvcc can neither contract a*b+c into an
-// FMA nor reassociate; prefix sums are the 32-lane Kogge-Stone scan a warp computes, chained
-// across 32-element tiles by a sequential carry. oracle/spec_sampler.c restates exactly this
-// order on the CPU, which is what makes the topic index of every token reproducible bit for bit.
+// FMA nor reassociate; prefix sums are built from the 32-lane Kogge-Stone scan a warp computes
+// (per-word prior rows: 32-element tiles chained by a sequential carry; a document's row: each lane
+// sums its own slots, one scan over the 32 lane totals). oracle/spec_sampler.c restates exactly
+// these orders on the CPU, which is what makes the topic index of every token reproducible bit for bit.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,6 +44,21 @@ __device__ __forceinline__ float warp_scan_inclusive(float v, int /*lane*/) {
   v = scan_step(v, 8);
   v = scan_step(v, 16);
   return v;
+}
+
+// Value of lane l-1, +0 for lane 0 (turns an inclusive warp scan into the exclusive one).
+__device__ __forceinline__ float shfl_up1_or_zero(float v) {
+  float out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .f32 y;\n\t"
+      "shfl.sync.up.b32 y|p, %1, 1, 0x0, 0xffffffff;\n\t"
+      "selp.f32 %0, y, 0f00000000, p;\n\t"
+      "}"
+      : "=f"(out)
+      : "f"(v));
+  return out;
 }
 
 // Philox4x32-10 (Salmon et al., SC'11): counter-based, so a token's draw depends only on

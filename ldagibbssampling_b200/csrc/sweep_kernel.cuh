@@ -117,8 +117,6 @@ struct WarpCtx {
   unsigned st_moved, st_prior;
 };
 
-__device__ __forceinline__ float scan_tile(float a, const WarpCtx&) { return warp_scan_inclusive(a, 0); }
-
 // Prior bucket: skip the own-token mass delta at topic o, then the fan-out-32 search.
 // The loads that depend only on (w, o) are taken off the dependent chain: P_w[o] is gathered once
 // per 32-token batch (one lane per token) and, for narrow rows, this lane's entry of the top search
@@ -180,7 +178,6 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
                                                 float qw, float po_l, int t) {
   const int lane = c.lane;
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
-  const int last_n = nnz - 32 * (NT - 1);  // active lanes of the last tile, 0..31
   constexpr bool kTopEarly = NT <= 3;  // wider rows have no register to spare for it (measured: C3 -8 %)
   float vtop = 0.0f;
   if (kTopEarly) vtop = prior_top_entry(p, c, w);
@@ -194,8 +191,10 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
   }
   // a live slot of topic o reads (o << 16) + count with 1 <= count <= 0xffff
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
-  float P[NT];
-  float carry = 0.0f;
+  // Lane-strided prefix: the lane sums its own slots tile by tile (from +0), ONE warp scan runs over
+  // the 32 lane totals, slot (g, lane) gets P = E_lane + s[g]. The cumulative order is lane-major.
+  float s[NT];
+  float run = 0.0f;
   int myjo = -1;
 #pragma unroll
   for (int g = 0; g < NT; ++g) {
@@ -205,20 +204,14 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
     const int n = max(nv[g] - ((int)is_old & c.excl), 0);
     const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
-    float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
-    a = scan_tile(a, c);
-    P[g] = fadd(carry, a);
-    carry = __shfl_sync(kFullMask, P[g], 31);
+    const float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
+    run = fadd(run, a);
+    s[g] = run;
   }
+  const float incl = warp_scan_inclusive(run, lane);
+  const float E = shfl_up1_or_zero(incl);
+  const float A = __shfl_sync(kFullMask, incl, 31);
   const int jo = __reduce_max_sync(kFullMask, myjo);
-  // A = inclusive prefix at slot nnz-1: in the last tile unless that tile is empty
-  float A;
-  if (NT == 1) {
-    A = __shfl_sync(kFullMask, P[0], (nnz - 1) & 31);
-  } else {
-    const float pl = last_n > 0 ? P[NT - 1] : P[NT - 2];
-    A = __shfl_sync(kFullMask, pl, (nnz - 1) & 31);
-  }
   float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
   delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
@@ -228,13 +221,16 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
   int newt;
   int jn = -1;  // slot of newt when it already has one
   if (x < A) {
-    jn = nnz - 1;
+    // First slot in cumulative (lane-major) order whose prefix exceeds x: the lowest lane with a
+    // hit and, prefixes being non-decreasing inside a lane, its count of non-hits. A padded slot
+    // repeats the prefix of the lane's slot before it, so it is never a lane's first hit unless the
+    // lane holds no slot of the row at all (the j < nnz test). No hit (x within an ulp of A): last slot.
+    int cnt = 0;
 #pragma unroll
-    for (int g = NT - 1; g >= 0; --g) {  // descending, so the lowest tile with a hit wins
-      // slot nnz-1 is a hit (x < A), so a padded slot, which sits above it, never comes first
-      const unsigned b = __ballot_sync(kFullMask, P[g] > x);
-      if (b) jn = (g << 5) + __ffs(b) - 1;
-    }
+    for (int g = 0; g < NT; ++g) cnt += (fadd(E, s[g]) > x) ? 0 : 1;
+    const int jc = (cnt << 5) + lane;
+    const unsigned b = __ballot_sync(kFullMask, (cnt < NT) && (jc < nnz));
+    jn = b ? __shfl_sync(kFullMask, jc, __ffs(b) - 1) : nnz - 1;
     newt = (int)(smem_u32(c.slots + jn) >> 16);  // shared memory still holds the row as loaded
   } else {
     ++c.st_prior;
@@ -337,10 +333,12 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
   float* pref = &smem_f32(c.pref);
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
   // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any is
-  // consumed, so a wide row pays one memory latency per group, not per tile.
+  // consumed, so a wide row pays one memory latency per group, not per tile. Same lane-strided
+  // prefix as the register path: pref[j] holds the lane-local inclusive sum s of slot j.
   const int ntiles = (nnz + 31) >> 5;
-  float carry = 0.0f, P = 0.0f;
-  int jo = 0;
+  const uint32_t okey = ((uint32_t)o << 16) + 1u;
+  float run = 0.0f;
+  int myjo = -1;
   for (int t0 = 0; t0 < ntiles; t0 += kGroup) {
     uint32_t sv[kGroup];
     int nv[kGroup];
@@ -357,25 +355,25 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
     }
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) {
-      if (t0 + g < ntiles) {
-        const int j = ((t0 + g) << 5) + lane;
-        const bool act = j < nnz;
+      const int j = ((t0 + g) << 5) + lane;
+      if (j < nnz) {
         const int topic = (int)(sv[g] >> 16);
-        const bool is_old = act && (topic == o);
-        const unsigned bo = __ballot_sync(kFullMask, is_old);
-        if (bo) jo = ((t0 + g) << 5) + __ffs(bo) - 1;
+        const bool is_old = (sv[g] - okey) < 0xffffu;
+        if (is_old) myjo = j;
         const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
         const int n = max(nv[g] - ((int)is_old & c.excl), 0);
         const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
-        float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);  // cc == 0 past nnz
-        a = scan_tile(a, c);
-        P = fadd(carry, a);
-        pref[j] = P;
-        carry = __shfl_sync(kFullMask, P, 31);
+        const float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
+        run = fadd(run, a);
+        pref[j] = run;
       }
     }
   }
-  const float A = __shfl_sync(kFullMask, P, (nnz - 1) & 31);
+  __syncwarp();
+  const float incl = warp_scan_inclusive(run, lane);
+  const float E = shfl_up1_or_zero(incl);
+  const float A = __shfl_sync(kFullMask, incl, 31);
+  const int jo = __reduce_max_sync(kFullMask, myjo);
   float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
   delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
@@ -386,15 +384,18 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
   int jn = -1;
   if (x < A) {
     jn = nnz - 1;
-    __syncwarp();
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int j = (tile << 5) + lane;
-      const bool hit = (j < nnz) && (pref[j] > x);
-      const unsigned b = __ballot_sync(kFullMask, hit);
-      if (b) {
-        jn = (tile << 5) + __ffs(b) - 1;
-        break;
+    // the lane's largest prefix is at its last slot of the row, where the local sum is `run`
+    const bool hitlane = (lane < nnz) && (fadd(E, run) > x);
+    const unsigned b = __ballot_sync(kFullMask, hitlane);
+    if (b) {
+      const int src = __ffs(b) - 1;
+      int cand = 0;
+      if (lane == src) {
+        int j = lane;
+        while (!(fadd(E, pref[j]) > x)) j += 32;  // ends at the lane's last slot at the latest
+        cand = j;
       }
+      jn = __shfl_sync(kFullMask, cand, src);
     }
     newt = (int)(slots[jn] >> 16);
   } else {

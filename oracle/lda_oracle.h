@@ -42,8 +42,12 @@ void oracle_count(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr, const
 void oracle_ndk_csr(int64_t D, int32_t K, const int64_t* doc_ptr, const int32_t* z,
                     int64_t* row_ptr /*D+1*/, int32_t* nnz /*D*/, int32_t* topic, int32_t* count);
 
-/* fp32 32-lane Kogge-Stone tile scan with sequential carry: the scan order of the spec. */
+/* fp32 32-lane Kogge-Stone tile scan with sequential carry: the scan order of the prior rows. */
 void oracle_tile_scan_f32(const float* in, int64_t n, float* out);
+
+/* Doc-bucket prefix order: slot j on lane j mod 32; each lane sums its slots tile by tile, one
+ * Kogge-Stone scan over the 32 lane totals; *total = scanned total of lane 31. */
+void oracle_lane_strided_prefix_f32(const float* in, int64_t n, float* out, float* total);
 
 /* Per-sweep tables from the sweep-start snapshot. prior is V*K inclusive prefix rows. */
 void oracle_spec_tables(int32_t V, int32_t K, const int32_t* nwk, const int32_t* nk,

@@ -55,6 +55,7 @@ def lib():
     L.oracle_count.argtypes = [C.c_int64, C.c_int32, C.c_int32, _i64p, _i32p, _i32p, _i32p, _i32p]
     L.oracle_ndk_csr.argtypes = [C.c_int64, C.c_int32, _i64p, _i32p, _i64p, _i32p, _i32p, _i32p]
     L.oracle_tile_scan_f32.argtypes = [_f32p, C.c_int64, _f32p]
+    L.oracle_lane_strided_prefix_f32.argtypes = [_f32p, C.c_int64, _f32p, C.POINTER(C.c_float)]
     L.oracle_spec_tables.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _f64p, C.c_double,
                                      _f32p, _f32p, _f32p, _f32p]
     L.oracle_spec_hsearch.restype = C.c_int32
@@ -179,6 +180,15 @@ def tile_scan(x):
     out = np.zeros_like(x)
     lib().oracle_tile_scan_f32(x, len(x), out)
     return out
+
+
+def lane_strided_prefix(x):
+    """Doc-bucket prefix order of the spec; returns (prefix per slot, scanned total of lane 31)."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(x)
+    total = C.c_float(0.0)
+    lib().oracle_lane_strided_prefix_f32(x, len(x), out, C.byref(total))
+    return out, np.float32(total.value)
 
 
 def spec_tables(nwk, nk, alpha, beta):

@@ -9,7 +9,8 @@
  * cmu_ron/TrainAndPredict.java:166, cmu/TrainAndPredict.java:265), split in
  * a sparse doc bucket  n_dk (n_wk+β)/(n_k+Vβ)  and a per-word prior bucket  α_k (n_wk+β)/(n_k+Vβ),
  * all in fp32 with every operation individually rounded (compile with -ffp-contract=off) and all
- * prefix sums in the 32-lane Kogge-Stone + sequential-carry order a warp produces.
+ * prefix sums in the order a warp produces them: 32-lane Kogge-Stone tiles with a sequential carry
+ * for the per-word prior rows, lane-strided sums + one Kogge-Stone scan for a document's row.
  * Same counts + same uniforms  =>  same topic index as the GPU, bit for bit.
  */
 #include <math.h>
@@ -77,6 +78,41 @@ void oracle_tile_scan_f32(const float* in, int64_t n, float* out) {
     for (int l = 0; l < 32 && base + l < n; ++l) out[base + l] = carry + x[l];
     carry = carry + x[31];
   }
+}
+
+/* Doc-bucket prefix order of the spec ("lane-strided"): slot j of a row of n slots sits on lane
+ * j mod 32, tile j div 32, as in the GPU's shared-memory row; NT = floor(n/32)+1 tiles (the row
+ * always has room for one more slot). Each lane sums ITS slots tile by tile starting from +0, the
+ * 32 lane totals go through the Kogge-Stone scan, and slot j gets  P_j = E_l + (lane-local
+ * inclusive sum), E_l = scanned total of lane l-1 (0 for lane 0). The cumulative order is
+ * therefore lane-major: (lane 0: slots 0, 32, 64, ...), (lane 1: slots 1, 33, ...), ...
+ * *total = the scanned total of lane 31. One warp scan per token whatever the row width. */
+void oracle_lane_strided_prefix_f32(const float* in, int64_t n, float* out, float* total) {
+  const int64_t nt = n / 32 + 1;
+  float T[32], y[32];
+  for (int l = 0; l < 32; ++l) {
+    float run = 0.0f;
+    for (int64_t g = 0; g < nt; ++g) {
+      const int64_t j = 32 * g + l;
+      if (j < n) {
+        run = run + in[j];
+        out[j] = run; /* lane-local for now */
+      }
+    }
+    T[l] = run;
+  }
+  for (int d = 1; d < 32; d <<= 1) {
+    for (int l = 0; l < 32; ++l) y[l] = (l >= d) ? (T[l] + T[l - d]) : T[l];
+    memcpy(T, y, sizeof(T));
+  }
+  for (int l = 0; l < 32; ++l) {
+    const float E = l == 0 ? 0.0f : T[l - 1];
+    for (int64_t g = 0; g < nt; ++g) {
+      const int64_t j = 32 * g + l;
+      if (j < n) out[j] = E + out[j];
+    }
+  }
+  *total = T[31];
 }
 
 void oracle_spec_tables(int32_t V, int32_t K, const int32_t* nwk, const int32_t* nk,
@@ -152,8 +188,8 @@ int32_t oracle_spec_select(int32_t K, const int32_t* slot_topic, const int32_t* 
     float y = x * invden[t];
     a[j] = y * (float)c;
   }
-  oracle_tile_scan_f32(a, nslots, S);
-  const float A = nslots > 0 ? S[nslots - 1] : 0.0f;
+  float A = 0.0f;
+  oracle_lane_strided_prefix_f32(a, nslots, S, &A);
   const float delta = ab[old_topic];
   float qp = q_w - delta;
   if (qp < 0.0f) qp = 0.0f;
@@ -161,12 +197,17 @@ int32_t oracle_spec_select(int32_t K, const int32_t* slot_topic, const int32_t* 
   const float x = u * T;
   int32_t result;
   if (x < A) {
+    /* first slot in cumulative (lane-major) order whose prefix exceeds x; none (x within an ulp
+     * of A): the row's last slot */
     int32_t j = nslots - 1;
-    for (int32_t i = 0; i < nslots; ++i)
-      if (S[i] > x) {
-        j = i;
-        break;
-      }
+    int found = 0;
+    for (int l = 0; l < 32 && !found; ++l)
+      for (int32_t i = l; i < nslots; i += 32)
+        if (S[i] > x) {
+          j = i;
+          found = 1;
+          break;
+        }
     result = slot_topic[j];
   } else {
     const float y = x - A;

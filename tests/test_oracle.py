@@ -60,6 +60,29 @@ def test_tile_scan_structure(oracle):
         assert np.array_equal(oracle.tile_scan(xi), np.cumsum(xi))
 
 
+def test_lane_strided_prefix_structure(oracle):
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 31, 32, 33, 63, 64, 100, 255, 256, 1000):
+        x = rng.random(n).astype(np.float32)
+        got, total = oracle.lane_strided_prefix(x)
+        # cumulative order is lane-major: slots 0, 32, 64, ..., then 1, 33, 65, ...
+        order = np.array([j for l in range(32) for j in range(l, n, 32)])
+        assert np.allclose(got[order], np.cumsum(x[order].astype(np.float64)), rtol=1e-5)
+        assert np.isclose(total, x.astype(np.float64).sum(), rtol=1e-5)
+        # lane 0 is a plain tile-by-tile fp32 sum of its own slots
+        run = np.float32(0)
+        for j in range(0, n, 32):
+            run = np.float32(run + x[j])
+            assert got[j] == run
+        # lane 1 starts from lane 0's total: P = E + local
+        if n > 1:
+            assert got[1] == np.float32(run + x[1])
+        # integers are exact in any order
+        xi = rng.integers(0, 100, n).astype(np.float32)
+        gi, ti = oracle.lane_strided_prefix(xi)
+        assert np.array_equal(gi[order], np.cumsum(xi[order])) and ti == xi.sum()
+
+
 def test_hsearch_matches_linear_search_on_monotone_rows(oracle):
     rng = np.random.default_rng(1)
     for K in (1, 7, 32, 33, 100, 1000, 1024, 1500, 5000):
