@@ -111,6 +111,8 @@ struct DeviceCorpus {
   // classes[i].shape.slot_cap slots; each class is one launch with shared memory sized to it.
   struct DocClass {
     int64_t begin = 0, end = 0;  // slice of doc_order
+    int64_t tokens = 0;          // tokens of those documents
+    int side_ctas = 0;           // > 0: background class, launched with this many CTAs on its own stream
     SweepShape shape;
   };
   std::vector<DocClass> classes;
@@ -129,6 +131,7 @@ struct b200lda_ctx {
 
   DeviceCorpus corp;  // training documents
   int min_row = 64;  // narrowest row-width class
+  int class_streams = 0;  // see launch_sweep
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
@@ -315,14 +318,47 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
     if (cap >= c->K || cap + 1 >= (int)len_ge.size()) return 0;
     return len_ge[(size_t)cap + 1];
   };
+  // tokens in documents of at least L tokens = L * len_ge[L] + sum_{M > L} len_ge[M]
+  std::vector<int64_t> suffix(len_ge.size() + 1, 0);
+  for (int L = (int)len_ge.size() - 1; L >= 0; --L) suffix[(size_t)L] = suffix[(size_t)L + 1] + len_ge[(size_t)L];
+  auto tokens_with_row_above = [&](int cap) -> int64_t {
+    if (cap >= c->K || cap + 1 >= (int)len_ge.size()) return 0;
+    return (int64_t)(cap + 1) * len_ge[(size_t)cap + 1] + suffix[(size_t)cap + 2];
+  };
+  const int64_t all_tokens = suffix[1];
   for (int i = (int)caps.size() - 1; i >= 0; --i) {
     DeviceCorpus::DocClass dc;
     dc.begin = docs_with_row_above(caps[i]);
     dc.end = i == 0 ? cp.D : docs_with_row_above(caps[i - 1]);
     if (dc.end <= dc.begin) continue;
+    dc.tokens = (i == 0 ? all_tokens : tokens_with_row_above(caps[i - 1])) - tokens_with_row_above(caps[i]);
     TRY(shape_for(c, caps[i], caps[i] > 256 ? 1 : 4, cp.max_doc_len, &dc.shape));
     cp.classes.push_back(dc);
   }
+  // Background classes. A class with too few documents to keep every resident warp busy several
+  // times over (the long tail: each document is one warp's serial chain) is bound by its longest
+  // documents, not by throughput. Alone it would idle the GPU; on a full-size grid beside the bulk
+  // it would take a register-file slot of 8 bulk warps on every SM for 2 of its own. So it runs on
+  // its own stream with just enough warps to finish in about half the time the bulk needs:
+  //   warps = 2 * (per-warp token latency ~2.5 us) * (bulk rate ~2.4e9 tokens/s) * share of tokens.
+  // Measured on the C4 shape (profiles/r01_tuning.md): full-size grids on forked streams 330 ms,
+  // everything on one stream 287 ms, at 738 M tokens; 36.1 vs 38.7 ms at 90 M tokens.
+  const size_t nc = cp.classes.size();
+  bool any_bulk = false;
+  for (size_t i = 0; i < nc; ++i) {
+    DeviceCorpus::DocClass& dc = cp.classes[i];
+    const int64_t resident_warps = (int64_t)dc.shape.ctas * dc.shape.warps_per_cta;
+    const bool background = i + 1 < nc && (dc.end - dc.begin) < 4 * resident_warps;
+    if (!background) {
+      any_bulk = true;
+      continue;
+    }
+    const double share = all_tokens > 0 ? (double)dc.tokens / (double)all_tokens : 1.0;
+    const int64_t warps = (int64_t)std::ceil(12000.0 * share);
+    const int64_t ctas = (warps + dc.shape.warps_per_cta - 1) / dc.shape.warps_per_cta;
+    dc.side_ctas = (int)std::max<int64_t>(c->sm_count / 8, std::min<int64_t>(dc.shape.ctas, ctas));
+  }
+  (void)any_bulk;
   return B200LDA_OK;
 }
 
@@ -543,7 +579,7 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
 
 template <int MODE, bool LIVE>
 int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
-                 unsigned long long* counter, cudaStream_t stream) {
+                 unsigned long long* counter, cudaStream_t stream, int max_ctas = 0) {
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
@@ -551,8 +587,9 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
   const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  const int grid_cap = max_ctas > 0 ? std::min(max_ctas, sh.ctas) : sh.ctas;
   const int ctas = (int)std::max<int64_t>(
-      1, std::min<int64_t>(sh.ctas, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
+      1, std::min<int64_t>(grid_cap, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
   const int threads = sh.warps_per_cta * 32;
 #define B200LDA_LAUNCH(TS, RC) k_gibbs_sweep<MODE, LIVE, TS, RC><<<ctas, threads, sh.smem, stream>>>(p)
   switch (rowclass_for(sh.slot_cap) * 2 + (sh.tables_in_smem ? 1 : 0)) {
@@ -580,15 +617,24 @@ int launch_sweep(b200lda_ctx* c, const DeviceCorpus& cp, const SweepParams& p) {
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
   if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
+  // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = background classes forked with their
+  // reduced grid, the bulk in sequence on the main stream (default); 1 = everything in sequence;
+  // 2 = every class forked at full size.
+  std::vector<bool> forked(n, false);
   for (size_t i = 0; i + 1 < n; ++i) {
-    CU(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
-    TRY((launch_class<MODE, LIVE>(c, p, cp.classes[i].shape, cp.classes[i].begin, cp.classes[i].end, c->d_sched + i,
-                                  c->side[i])));
-    CU(cudaEventRecord(c->ev_join[i], c->side[i]));
+    const DeviceCorpus::DocClass& dc = cp.classes[i];
+    const bool fork = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
+    forked[i] = fork;
+    cudaStream_t st = fork ? c->side[i] : c->stream;
+    if (fork) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+    TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i, st,
+                                  c->class_streams == 0 ? dc.side_ctas : 0)));
+    if (fork) CU(cudaEventRecord(c->ev_join[i], st));
   }
   TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
                                 c->d_sched + (n - 1), c->stream)));
-  for (size_t i = 0; i + 1 < n; ++i) CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+  for (size_t i = 0; i + 1 < n; ++i)
+    if (forked[i]) CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   return B200LDA_OK;
 }
 
@@ -694,6 +740,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
     const int v = atoi(e);
     if (v >= 32) c->min_row = round_up32(v);
   }
+  if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {

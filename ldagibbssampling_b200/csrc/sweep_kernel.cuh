@@ -84,6 +84,9 @@ __host__ __device__ constexpr size_t sweep_smem_per_warp(int slot_cap) {
   return (size_t)kSmemBytesPerSlot * (size_t)slot_cap + sizeof(uint32_t) * kRowPad;
 }
 
+#ifndef B200LDA_TOP_EARLY_NT
+#define B200LDA_TOP_EARLY_NT 3  // rows of up to this many tiles request the prior's top level at the start of the token step
+#endif
 #ifndef B200LDA_SWEEP_MIN_CTAS
 #define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
 #endif
@@ -178,7 +181,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
                                                 float qw, float po_l, int t) {
   const int lane = c.lane;
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
-  constexpr bool kTopEarly = NT <= 3;  // wider rows have no register to spare for it (measured: C3 -8 %)
+  constexpr bool kTopEarly = NT <= B200LDA_TOP_EARLY_NT;
   float vtop = 0.0f;
   if (kTopEarly) vtop = prior_top_entry(p, c, w);
   uint32_t sv[NT];
