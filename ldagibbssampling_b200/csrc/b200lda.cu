@@ -146,7 +146,8 @@ struct b200lda_ctx {
   unsigned long long* d_sched = nullptr;  // [kMaxClasses] document scheduler counter per class launch
   // side streams so the row-width classes of one sweep run concurrently (fork/join by events)
   cudaStream_t side[kMaxClasses] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[kMaxClasses] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxClasses] = {}, ev_bulk = nullptr;
+  const void* timed_corpus = nullptr;  // corpus whose last sweep left ev_fork / ev_bulk / ev_join to read
   int* d_bad = nullptr;
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
@@ -310,6 +311,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
 // len_ge[L] = number of documents with at least L tokens (documents are ordered longest first).
 int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>& len_ge) {
   cp.classes.clear();
+  if (c->timed_corpus == &cp) c->timed_corpus = nullptr;  // the classes the pending timings describe are gone
   const int widest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
   std::vector<int> caps;
   for (int cap = c->min_row; cap < widest; cap *= 2) caps.push_back(cap);
@@ -340,7 +342,8 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
   // documents, not by throughput. Alone it would idle the GPU; on a full-size grid beside the bulk
   // it would take a register-file slot of 8 bulk warps on every SM for 2 of its own. So it runs on
   // its own stream with just enough warps to finish in about half the time the bulk needs:
-  //   warps = 2 * (per-warp token latency ~2.5 us) * (bulk rate ~2.4e9 tokens/s) * share of tokens.
+  //   warps = 2 * (per-warp token latency ~2.5 us) * (bulk rate ~2.4e9 tokens/s) * share of tokens
+  // as a first guess (doubled below), corrected sweep by sweep from the measured finish times.
   // Measured on the C4 shape (profiles/r01_tuning.md): full-size grids on forked streams 330 ms,
   // everything on one stream 287 ms, at 738 M tokens; 36.1 vs 38.7 ms at 90 M tokens.
   const size_t nc = cp.classes.size();
@@ -354,7 +357,7 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
       continue;
     }
     const double share = all_tokens > 0 ? (double)dc.tokens / (double)all_tokens : 1.0;
-    const int64_t warps = (int64_t)std::ceil(12000.0 * share);
+    const int64_t warps = (int64_t)std::ceil(24000.0 * share);  // first guess, 2x margin; retune_background follows the clock
     const int64_t ctas = (warps + dc.shape.warps_per_cta - 1) / dc.shape.warps_per_cta;
     dc.side_ctas = (int)std::max<int64_t>(c->sm_count / 8, std::min<int64_t>(dc.shape.ctas, ctas));
   }
@@ -606,20 +609,48 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   return B200LDA_OK;
 }
 
-// One pass over a corpus = one launch per row-width class, all in flight together: the wide
-// classes (few, long documents: each a long serial chain on one warp) go to side streams forked
-// off the context's stream, the bulk runs on the context's stream, and the sweep joins them. A
-// long document's latency is then hidden behind the bulk instead of being a launch of its own.
+// Background grids follow the clock: after a sweep, compare when each background class finished
+// with when the bulk did (events of that sweep, read only if already complete: no synchronisation)
+// and double a grid that finished late, shrink one that finished in under a third of the bulk's
+// time. The first guess (configure_sweep) assumes K ~ 1000; at K = 10 000 a token of a long document
+// costs several times more (three dependent table levels) and the guess is 8x too small.
+void retune_background(b200lda_ctx* c, DeviceCorpus& cp) {
+  if (c->timed_corpus != &cp || c->class_streams != 0) return;
+  c->timed_corpus = nullptr;
+  const size_t n = cp.classes.size();
+  if (cudaEventQuery(c->ev_bulk) != cudaSuccess) return;
+  float t_bulk = 0.0f;
+  if (cudaEventElapsedTime(&t_bulk, c->ev_fork, c->ev_bulk) != cudaSuccess) return;
+  for (size_t i = 0; i + 1 < n; ++i) {
+    DeviceCorpus::DocClass& dc = cp.classes[i];
+    if (dc.side_ctas <= 0) continue;
+    float t_bg = 0.0f;
+    if (cudaEventQuery(c->ev_join[i]) != cudaSuccess ||
+        cudaEventElapsedTime(&t_bg, c->ev_fork, c->ev_join[i]) != cudaSuccess)
+      continue;
+    if (t_bg > 0.9f * t_bulk)
+      dc.side_ctas = std::min(dc.shape.ctas, std::max(dc.side_ctas + 1, dc.side_ctas * 2));
+    else if (t_bg < 0.35f * t_bulk)
+      dc.side_ctas = std::max(std::max(1, c->sm_count / 8), dc.side_ctas * 3 / 4);
+  }
+  (void)cudaGetLastError();
+}
+
+// One pass over a corpus = one launch per row-width class. The bulk classes run one after the
+// other on the context's stream, each filling the GPU. The long-tail classes (few, long documents:
+// each a long serial chain on one warp) run in the background on side streams forked off the
+// context's stream with a reduced grid, and the sweep joins them: a long document's latency is
+// hidden behind the bulk, and its CTAs do not take bulk CTAs' register-file slots on every SM.
 template <int MODE, bool LIVE>
-int launch_sweep(b200lda_ctx* c, const DeviceCorpus& cp, const SweepParams& p) {
+int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p) {
+  retune_background(c, cp);
   CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
   CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
   if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
-  // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = background classes forked with their
-  // reduced grid, the bulk in sequence on the main stream (default); 1 = everything in sequence;
-  // 2 = every class forked at full size.
+  // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = the policy above (default);
+  // 1 = everything in sequence; 2 = every class forked at full size.
   std::vector<bool> forked(n, false);
   for (size_t i = 0; i + 1 < n; ++i) {
     const DeviceCorpus::DocClass& dc = cp.classes[i];
@@ -633,6 +664,10 @@ int launch_sweep(b200lda_ctx* c, const DeviceCorpus& cp, const SweepParams& p) {
   }
   TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
                                 c->d_sched + (n - 1), c->stream)));
+  if (n > 1) {
+    CU(cudaEventRecord(c->ev_bulk, c->stream));
+    c->timed_corpus = &cp;
+  }
   for (size_t i = 0; i + 1 < n; ++i)
     if (forked[i]) CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
   return B200LDA_OK;
@@ -758,10 +793,10 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   {
     int lo = 0, hi = 0;  // wide-row classes get the higher priority: their chains are the critical path
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    bool ok = cudaEventCreate(&c->ev_fork) == cudaSuccess && cudaEventCreate(&c->ev_bulk) == cudaSuccess;
     for (int i = 0; i < kMaxClasses && ok; ++i)
       ok = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
-           cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreate(&c->ev_join[i]) == cudaSuccess;
     if (!ok) return bail(fail(B200LDA_ECUDA, "creating side streams failed"));
   }
   const size_t VK = (size_t)c->V * c->K;
@@ -815,6 +850,7 @@ void b200lda_destroy(b200lda_ctx* c) {
   for (auto& e : c->ev_pool)
     if (e) cudaEventDestroy(e);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_bulk) cudaEventDestroy(c->ev_bulk);
   for (int i = 0; i < kMaxClasses; ++i) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     if (c->side[i]) cudaStreamDestroy(c->side[i]);
@@ -1021,6 +1057,7 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
   double* d_theta = nullptr;
   auto cleanup = [&](int code) {
     cudaStreamSynchronize(c->stream);
+    if (c->timed_corpus == &cp) c->timed_corpus = nullptr;
     free_corpus(cp);
     dev_free(d_acc);
     dev_free(d_theta);
