@@ -55,14 +55,14 @@ struct SweepParams {
   PriorLayout layout;
   int K;
   int slot_cap;               // shared-memory slots per warp (multiple of 32)
-  int doc_chunk;              // documents fetched per scheduler atomic
+  int doc_chunk;              // documents fetched per scheduler atomic (strided through doc_order)
   int exclude_self;           // 1: the token being resampled is counted in n_wk (training);
                               // 0: held-out inference against frozen counts (TopicInferencer)
   float beta_f;
   uint64_t seed;
   uint32_t sweep;
   int64_t global_tok_off;
-  unsigned long long* doc_counter;  // dynamic document scheduler (starts at 0 for each launch)
+  unsigned long long* doc_counter;  // dynamic document scheduler: next chunk index (starts at 0 for each launch)
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
 };
@@ -500,15 +500,20 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
   const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
 
+  // Dynamic scheduler: one atomic fetches a chunk of doc_chunk documents. Documents are ordered
+  // longest first, so a chunk is STRIDED through that order (chunk ci = documents ci, ci + nchunks,
+  // ci + 2 nchunks, ...): every chunk holds one document of each length band instead of the first
+  // chunk holding the doc_chunk longest documents of the class (measured on C1, where that chunk
+  // alone was the whole sweep: 1.6 -> 0.6 ms).
+  const unsigned long long nchunks = (ndocs + (unsigned long long)p.doc_chunk - 1) / (unsigned long long)p.doc_chunk;
   for (;;) {
-    unsigned long long c0 = 0;
-    if (lane == 0) c0 = atomicAdd(p.doc_counter, (unsigned long long)p.doc_chunk);
-    c0 = __shfl_sync(kFullMask, c0, 0);
-    if (c0 >= ndocs) break;
-    const unsigned long long c1 = min(c0 + (unsigned long long)p.doc_chunk, ndocs);
+    unsigned long long ci = 0;
+    if (lane == 0) ci = atomicAdd(p.doc_counter, 1ull);
+    ci = __shfl_sync(kFullMask, ci, 0);
+    if (ci >= nchunks) break;
 
-    for (unsigned long long ci = c0; ci < c1; ++ci) {
-      const int64_t d = (int64_t)__ldg(p.doc_order + p.order_begin + (int64_t)ci);
+    for (unsigned long long di = ci; di < ndocs; di += nchunks) {
+      const int64_t d = (int64_t)__ldg(p.doc_order + p.order_begin + (int64_t)di);
       const int64_t tb = p.doc_ptr[d], te = p.doc_ptr[d + 1];
       if (te == tb) continue;
       const int64_t rp = p.row_ptr[d];
