@@ -240,3 +240,28 @@ def test_edge_shapes_match_oracle(oracle, K, V, lens):
     assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
     ll = oracle.loglik(dp, tok, want, V, K, ALPHA, BETA)
     assert abs(s.loglik() - ll) <= 1e-9 * abs(ll)
+
+
+def test_launch_policy_does_not_change_deferred_results(oracle, monkeypatch):
+    """Row-width classes run as bulk launches in sequence plus background launches whose grid is
+    retuned every sweep from event timings. None of that may show in DEFERRED results: same chain,
+    bit for bit, with the classes forked at full size, all in sequence, or under the default
+    policy, and equal to the oracle. The corpus has a long-document tail (several classes)."""
+    rng = np.random.default_rng(5)
+    V, K = 600, 700
+    lens = np.concatenate([rng.integers(20, 120, 900), rng.integers(300, 700, 12), [1500, 2200]]).astype(np.int64)
+    rng.shuffle(lens)
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z0 = oracle.init_z(len(tok), K, 4)
+    want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 4, 1, 6)
+    classes = None
+    for policy in ("0", "1", "2"):
+        monkeypatch.setenv("B200LDA_CLASS_STREAMS", policy)
+        s = _sampler(K, V, seed=4)
+        s.load_corpus(dp, tok)
+        s.init_assignments(z0)
+        s.sweep(6)
+        assert np.array_equal(s.assignments(), want), f"policy {policy}"
+        classes = s.stats()["row_classes"]
+    assert classes >= 3
