@@ -116,6 +116,7 @@ struct DeviceCorpus {
     SweepShape shape;
   };
   std::vector<DocClass> classes;
+  int tune_waits = 0;  // sweeps after which the host still waits for the timings (retune_background)
 };
 
 }  // namespace
@@ -311,6 +312,7 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
 // len_ge[L] = number of documents with at least L tokens (documents are ordered longest first).
 int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>& len_ge) {
   cp.classes.clear();
+  cp.tune_waits = 8;
   if (c->timed_corpus == &cp) c->timed_corpus = nullptr;  // the classes the pending timings describe are gone
   const int widest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
   std::vector<int> caps;
@@ -614,11 +616,24 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
 // and double a grid that finished late, shrink one that finished in under a third of the bulk's
 // time. The first guess (configure_sweep) assumes K ~ 1000; at K = 10 000 a token of a long document
 // costs several times more (three dependent table levels) and the guess is 8x too small.
+// Sweeps are enqueued without host synchronisation, so the previous sweep's events are normally
+// still pending here; for the first tune_waits sweeps of a corpus the host waits for them (the
+// grids settle within a handful of sweeps), afterwards it only uses timings that happen to be ready.
 void retune_background(b200lda_ctx* c, DeviceCorpus& cp) {
   if (c->timed_corpus != &cp || c->class_streams != 0) return;
   c->timed_corpus = nullptr;
   const size_t n = cp.classes.size();
-  if (cudaEventQuery(c->ev_bulk) != cudaSuccess) return;
+  bool any_background = false;
+  for (size_t i = 0; i + 1 < n; ++i) any_background = any_background || cp.classes[i].side_ctas > 0;
+  if (!any_background) return;
+  if (cudaEventQuery(c->ev_bulk) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (cp.tune_waits <= 0) return;
+    --cp.tune_waits;
+    if (cudaEventSynchronize(c->ev_bulk) != cudaSuccess) return;
+    for (size_t i = 0; i + 1 < n; ++i)
+      if (cp.classes[i].side_ctas > 0 && cudaEventSynchronize(c->ev_join[i]) != cudaSuccess) return;
+  }
   float t_bulk = 0.0f;
   if (cudaEventElapsedTime(&t_bulk, c->ev_fork, c->ev_bulk) != cudaSuccess) return;
   for (size_t i = 0; i + 1 < n; ++i) {
