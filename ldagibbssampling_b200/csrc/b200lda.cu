@@ -349,21 +349,16 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
   // Measured on the C4 shape (profiles/r01_tuning.md): full-size grids on forked streams 330 ms,
   // everything on one stream 287 ms, at 738 M tokens; 36.1 vs 38.7 ms at 90 M tokens.
   const size_t nc = cp.classes.size();
-  bool any_bulk = false;
   for (size_t i = 0; i < nc; ++i) {
     DeviceCorpus::DocClass& dc = cp.classes[i];
     const int64_t resident_warps = (int64_t)dc.shape.ctas * dc.shape.warps_per_cta;
     const bool background = i + 1 < nc && (dc.end - dc.begin) < 4 * resident_warps;
-    if (!background) {
-      any_bulk = true;
-      continue;
-    }
+    if (!background) continue;
     const double share = all_tokens > 0 ? (double)dc.tokens / (double)all_tokens : 1.0;
     const int64_t warps = (int64_t)std::ceil(24000.0 * share);  // first guess, 2x margin; retune_background follows the clock
     const int64_t ctas = (warps + dc.shape.warps_per_cta - 1) / dc.shape.warps_per_cta;
     dc.side_ctas = (int)std::max<int64_t>(c->sm_count / 8, std::min<int64_t>(dc.shape.ctas, ctas));
   }
-  (void)any_bulk;
   return B200LDA_OK;
 }
 
