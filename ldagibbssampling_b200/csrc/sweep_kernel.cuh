@@ -147,7 +147,7 @@ __device__ __forceinline__ float prior_top_entry(const SweepParams& p, const War
   const float* prow = p.prior + (size_t)w * p.layout.stride;
   return (c.top_lane >= 0) ? __ldg(prow + c.top_lane) : 0.0f;
 }
-__device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int w, float po, float y, float delta,
+__device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int K, int w, float po, float y, float delta,
                                             float vtop) {
   const float* prow = p.prior + (size_t)w * p.layout.stride;
   const float pod = fsub(po, delta);
@@ -156,11 +156,19 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int 
   const int ntop = p.layout.size[top];  // <= 32
   const unsigned bt = __ballot_sync(kFullMask, (lane < ntop) && (vtop > s));
   int block = bt ? (__ffs(bt) - 1) : (ntop - 1);
-  for (int lev = top - 1; lev >= 0; --lev) {
+  for (int lev = top - 1; lev >= 1; --lev) {  // middle levels (K > 1024 only)
     const int lo = block << 5;
     const int nvalid = min(32, p.layout.size[lev] - lo);
     float v = 0.0f;
     if (lane < nvalid) v = __ldg(prow + p.layout.off[lev] + lo + lane);
+    const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
+    block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
+  }
+  if (top >= 1) {  // level 0: the K prefix sums themselves, at offset 0 of the word's block
+    const int lo = block << 5;
+    const int nvalid = min(32, K - lo);
+    float v = 0.0f;
+    if (lane < nvalid) v = __ldg(prow + lo + lane);
     const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
     block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
   }
@@ -194,12 +202,12 @@ __device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx&
 // behind slot_cap): a padded slot reads topic 0 / count 0, weighs exactly +0 and can never be the
 // old topic's slot, so loads, weights and the bucket search carry no per-lane validity predicate.
 // Prefixes stay in registers; the row edit happens in shared memory.
-template <int NT, int MODE, bool LIVE, bool TS>
+template <int NT, int MODE, bool LIVE, bool TS, int TE>
 __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
                                                 float qw, float po_l, int t) {
   const int lane = c.lane;
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
-  constexpr bool kTopEarly = NT <= B200LDA_TOP_EARLY_NT;
+  constexpr bool kTopEarly = NT <= TE;  // request the prior's top level before the bucket is known
   float vtop = 0.0f;
   if (kTopEarly) vtop = prior_top_entry(p, c, w);
   uint32_t sv[NT];
@@ -256,7 +264,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
   } else {
     ++c.st_prior;
     if (!kTopEarly) vtop = prior_top_entry(p, c, w);
-    newt = prior_search(p, lane, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, vtop);
+    newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, vtop);
   }
 
   if (MODE == MODE_UPDATE && newt != o) {
@@ -421,7 +429,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
     newt = (int)(slots[jn] >> 16);
   } else {
     ++c.st_prior;
-    newt = prior_search(p, lane, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, c, w));
+    newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, c, w));
   }
 
   if (MODE == MODE_UPDATE && newt != o) {
@@ -485,6 +493,10 @@ __host__ __device__ constexpr int rowclass_min_ctas(int rc) {
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM, int ROWCLASS>
 __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_sweep(const SweepParams p) {
   constexpr int MAXNT = rowclass_max_tiles(ROWCLASS);
+  // Rows up to kTE tiles request the prior's top search level at the start of the token step. The
+  // <= 128-slot classes have the register for it at any width; in the wide class it costs more
+  // than it hides beyond 3 tiles (measured: C4 +1.3 % / C3 -2 % when applied everywhere).
+  constexpr int kTE = ROWCLASS <= 1 ? 5 : B200LDA_TOP_EARLY_NT;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -566,14 +578,14 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
           doc_nnz += (unsigned)nnz;
           int newt;
           const int tile_case = nnz >> 5;  // tiles needed for nnz + 1 slots, minus one (uniform across the warp)
-          if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
+          if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+          else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
           else newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
           if (lane == t) new_l = newt;
         }
