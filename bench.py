@@ -131,6 +131,17 @@ class ClockSampler:
 # CPU arm: the Mallet-faithful oracle port on the host cores (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------
 
+def host_cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
 def run_cpu(workload, K, cpu_docs, warmup, steps=None, seconds=None):
     """Times AD-LDA sweeps of oracle/mallet_sparse_lda.c with T = all host threads on a bounded
     sample (cpu_docs documents of the workload's shape). Returns (tokens/s, ms_per_step, info)."""
@@ -160,7 +171,8 @@ def run_cpu(workload, K, cpu_docs, warmup, steps=None, seconds=None):
     total = sum(times)
     info = {"cores": threads, "kind": "port",
             "sample": f"{cpu_docs} docs / {n} tokens of the {workload} shape (V={V}, K={K}), "
-                      f"{warmup} warm-up + {len(times)} timed AD-LDA sweeps, T={threads} worker replicas",
+                      f"{warmup} warm-up + {len(times)} timed AD-LDA sweeps, T={threads} worker replicas "
+                      f"on {threads} x {host_cpu_model()}",
             "ll_per_token": ll}
     return n * len(times) / total, 1e3 * total / len(times), info
 
