@@ -138,6 +138,37 @@ def test_spec_sampler_draws_from_the_textbook_conditional(oracle):
             i += 1
 
 
+@pytest.mark.parametrize("K,doc_len", [(100, 400), (300, 900)])
+def test_spec_sampler_on_wide_rows_draws_from_the_spec_conditional(oracle, K, doc_len):
+    """Rows wider than one tile (3 and 5+ tiles): the lane-strided cumulative order is a permutation of
+    the slots, so as a sampler it must still map a fraction p_k of the uniforms to topic k, where
+    p_k ∝ (n_wk - [k=o] + β)(n_dk - [k=o] + α_k) / (n_k + Vβ) with the sweep-start n_k of the spec
+    (own token not excluded there). Computed here in float64, independently of the C code."""
+    rng = np.random.default_rng(K)
+    V = 40
+    dp = np.array([0, doc_len, doc_len + 2000], np.int64)  # the wide document + filler that populates n_wk
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z = rng.integers(0, K, int(dp[-1])).astype(np.int32)
+    alpha = np.full(K, ALPHA)
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    invden, ab, prior, q = oracle.spec_tables(nwk, nk, alpha, BETA)
+    ndk = np.bincount(z[:doc_len], minlength=K)
+    st = np.nonzero(ndk)[0].astype(np.int32)
+    sc = ndk[st].astype(np.int32)
+    assert len(st) > 64
+    G = 20000
+    grid = (np.arange(G, dtype=np.float64) + 0.5) / G
+    for t in (0, doc_len // 2, doc_len - 1):
+        w, o = int(tok[t]), int(z[t])
+        excl = (np.arange(K) == o).astype(np.float64)
+        p = (nwk[w] - excl + BETA) * (ndk - excl + alpha) / (nk + V * BETA)
+        p /= p.sum()
+        picks = np.array([oracle.spec_select(K, st, sc, nwk[w], invden, ab, prior[w], q[w], BETA, o, u) for u in grid])
+        freq = np.bincount(picks, minlength=K) / G
+        # each topic owns at most two intervals of u (doc bucket, prior bucket): four edges of 1/G each
+        assert np.abs(freq - p).max() < 6.0 / G + 1e-5
+
+
 def test_frozen_triples_regression(oracle):
     g = np.load(os.path.join(GOLD, "frozen_triples.npz"))
     for name in ("k4", "k20", "k100", "k1500"):
