@@ -133,6 +133,7 @@ struct b200lda_ctx {
   DeviceCorpus corp;  // training documents
   int min_row = 64;  // narrowest row-width class
   int class_streams = 0;  // see launch_sweep
+  bool infer_fused = true;  // b200lda_infer: all iterations of a document in one kernel visit (B200LDA_INFER_FUSED=0: one launch set per iteration)
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
@@ -259,17 +260,19 @@ int rowclass_for(int slot_cap) { return slot_cap <= 64 ? 0 : slot_cap <= 128 ? 1
 // Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
 // of slot_cap entries each.
 int occupancy_of(bool ts, int rc, int threads, size_t smem, int* out) {
-  int occ[3] = {0, 0, 0};
+  int occ[4] = {0, 0, 0, 0};
   if (ts) {
     TRY((sweep_occupancy<MODE_UPDATE, true, true>(rc, threads, smem, &occ[0])));
     TRY((sweep_occupancy<MODE_UPDATE, false, true>(rc, threads, smem, &occ[1])));
     TRY((sweep_occupancy<MODE_FROZEN, false, true>(rc, threads, smem, &occ[2])));
+    TRY((sweep_occupancy<MODE_INFER, false, true>(rc, threads, smem, &occ[3])));
   } else {
     TRY((sweep_occupancy<MODE_UPDATE, true, false>(rc, threads, smem, &occ[0])));
     TRY((sweep_occupancy<MODE_UPDATE, false, false>(rc, threads, smem, &occ[1])));
     TRY((sweep_occupancy<MODE_FROZEN, false, false>(rc, threads, smem, &occ[2])));
+    TRY((sweep_occupancy<MODE_INFER, false, false>(rc, threads, smem, &occ[3])));
   }
-  *out = std::min(occ[0], std::min(occ[1], occ[2]));
+  *out = std::min(std::min(occ[0], occ[1]), std::min(occ[2], occ[3]));
   return B200LDA_OK;
 }
 
@@ -786,6 +789,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
     if (v >= 32) c->min_row = round_up32(v);
   }
   if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
+  if (const char* e = std::getenv("B200LDA_INFER_FUSED")) c->infer_fused = atoi(e) != 0;
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {
@@ -1083,24 +1087,44 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
   if ((rc = build_doc_rows(c, cp))) return cleanup(rc);
   if ((rc = build_tables(c))) return cleanup(rc);
   int samples = 0;
-  for (int32_t it = 1; it <= iterations; ++it) {
-    SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, (uint32_t)it);
+  for (int32_t it = 1; it <= iterations; ++it)
+    if (it > burn_in && (it - burn_in) % thinning == 0) ++samples;
+  if (c->infer_fused && iterations >= 1) {
+    // n_wk / n_k are frozen, so every document is an independent chain: one launch set in which a
+    // warp runs all iterations of its document (row resident in shared memory, samples added to
+    // d_acc as they are reached) replaces `iterations` launch sets + accumulate passes. Same
+    // Philox keys (sweep = iteration), so the result is the per-iteration schedule's, bit for bit.
+    SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, 0u);
     p.exclude_self = 0;  // the held-out tokens are not part of n_wk / n_k
     p.stats_cum = c->d_counters + 9;
     p.seed = seed;
     p.global_tok_off = 0;
-    if ((rc = launch_sweep<MODE_UPDATE, false>(c, cp, p))) return cleanup(rc);
-    if (it > burn_in && (it - burn_in) % thinning == 0) {
+    p.infer_iters = iterations;
+    p.infer_burn_in = burn_in;
+    p.infer_thinning = thinning;
+    p.infer_samples = samples;
+    p.infer_acc = d_acc;
+    if ((rc = launch_sweep<MODE_INFER, false>(c, cp, p))) return cleanup(rc);
+    if (samples == 0) samples = 1;  // Mallet: no sample saved -> the final state (added by the kernel)
+  } else {
+    for (int32_t it = 1; it <= iterations; ++it) {
+      SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, (uint32_t)it);
+      p.exclude_self = 0;
+      p.stats_cum = c->d_counters + 9;
+      p.seed = seed;
+      p.global_tok_off = 0;
+      if ((rc = launch_sweep<MODE_UPDATE, false>(c, cp, p))) return cleanup(rc);
+      if (it > burn_in && (it - burn_in) % thinning == 0) {
+        k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr,
+                                                                               cp.d_row_nnz, cp.d_rows, d_acc);
+        c->launches += 1;
+      }
+    }
+    if (samples == 0) {  // Mallet: no sample saved -> use the final state
       k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
                                                                              cp.d_rows, d_acc);
-      c->launches += 1;
-      ++samples;
+      samples = 1;
     }
-  }
-  if (samples == 0) {  // Mallet: no sample saved -> use the final state
-    k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
-                                                                           cp.d_rows, d_acc);
-    samples = 1;
   }
   k_infer_theta<<<grid_for(c, (int64_t)DK, 256), 256, 0, c->stream>>>(num_docs, c->K, samples, cp.d_doc_ptr, d_acc, c->d_alpha,
                                                                      c->alpha_sum, d_theta);

@@ -26,13 +26,16 @@
 // row-width class so that per-warp shared memory follows the row width.
 // MODE_UPDATE serves LIVE (LIVE=true: n_wk read through L1/L2 and written in place) and DEFERRED
 // (LIVE=false: frozen n_wk through the read-only path, moves go to a second buffer);
-// MODE_FROZEN moves nothing (north-star parity mode).
+// MODE_FROZEN moves nothing (north-star parity mode). MODE_INFER is held-out inference
+// (TopicInferencer.getSampledDistribution): n_wk / n_k are frozen, so documents are independent
+// chains and a warp runs ALL iterations of its document in one visit, the row staying in shared
+// memory, adding the row to the document's sample accumulator at every saved iteration.
 #pragma once
 #include "device_common.cuh"
 
 namespace b200lda {
 
-enum { MODE_UPDATE = 0, MODE_FROZEN = 1 };
+enum { MODE_UPDATE = 0, MODE_FROZEN = 1, MODE_INFER = 2 };
 
 struct SweepParams {
   const int32_t* doc_order;   // [D] document ids, longest first
@@ -65,6 +68,11 @@ struct SweepParams {
   unsigned long long* doc_counter;  // dynamic document scheduler: next chunk index (starts at 0 for each launch)
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
+  // MODE_INFER: iterations 1..infer_iters per document (Philox sweep key = iteration); a sample is
+  // saved when it > burn_in and (it - burn_in) % thinning == 0, or after the last iteration when
+  // no iteration qualifies (infer_samples == 0): acc[d, k] += n_dk.
+  int infer_iters, infer_burn_in, infer_thinning, infer_samples;
+  int32_t* infer_acc;               // [D * K]
 };
 
 #ifndef B200LDA_SWEEP_GROUP
@@ -267,7 +275,7 @@ __device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c
     newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, vtop);
   }
 
-  if (MODE == MODE_UPDATE && newt != o) {
+  if (MODE != MODE_FROZEN && newt != o) {
     ++c.st_moved;
     int pos = 0;  // #slots with topic < newt (old slot still present); only needed when newt is new to the row
     if (jn < 0) {
@@ -432,7 +440,7 @@ __device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx&
     newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, c, w));
   }
 
-  if (MODE == MODE_UPDATE && newt != o) {
+  if (MODE != MODE_FROZEN && newt != o) {
     ++c.st_moved;
     // Where does newt live (or go) in the row as it stands, old slot still present?
     int pos = 0;
@@ -552,54 +560,74 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
       __syncwarp();
       unsigned doc_nnz = 0;
 
-      for (int64_t base = tb; base < te; base += 32) {
-        const int64_t i = base + lane;
-        const bool valid = i < te;
-        const int w_l = valid ? __ldg(p.tok_word + i) : 0;
-        const int o_l = valid ? (int)p.z[i] : 0;
-        float u_l = 0.0f;
-        if (valid) {
-          if (p.uniforms) {
-            u_l = __ldg(p.uniforms + i);
-          } else {
-            u_l = u24(token_random(p.seed, (uint64_t)(p.global_tok_off + i), p.sweep, 0u).x);
+      const int iters = MODE == MODE_INFER ? p.infer_iters : 1;
+      for (int it = 1; it <= iters; ++it) {
+        const uint32_t sweep_key = MODE == MODE_INFER ? (uint32_t)it : p.sweep;
+        for (int64_t base = tb; base < te; base += 32) {
+          const int64_t i = base + lane;
+          const bool valid = i < te;
+          const int w_l = valid ? __ldg(p.tok_word + i) : 0;
+          const int o_l = valid ? (int)p.z[i] : 0;
+          float u_l = 0.0f;
+          if (valid) {
+            if (p.uniforms) {
+              u_l = __ldg(p.uniforms + i);
+            } else {
+              u_l = u24(token_random(p.seed, (uint64_t)(p.global_tok_off + i), sweep_key, 0u).x);
+            }
+          }
+          const float q_l = valid ? __ldg(p.q + w_l) : 0.0f;
+          const float po_l = valid ? __ldg(p.prior + (size_t)w_l * p.layout.stride + o_l) : 0.0f;  // P_w[o]
+          int new_l = o_l;
+          const int cnt = (int)min((int64_t)32, te - base);
+
+          for (int t = 0; t < cnt; ++t) {
+            const int w = __shfl_sync(kFullMask, w_l, t);
+            const int o = __shfl_sync(kFullMask, o_l, t);
+            const float u = __shfl_sync(kFullMask, u_l, t);
+            const float qw = __shfl_sync(kFullMask, q_l, t);
+            doc_nnz += (unsigned)nnz;
+            int newt;
+            const int tile_case = nnz >> 5;  // tiles needed for nnz + 1 slots, minus one (uniform across the warp)
+            if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
+            else newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
+            if (lane == t) new_l = newt;
+          }
+
+          if (valid) {
+            if (MODE == MODE_FROZEN) {
+              p.z_out[i] = new_l;
+            } else if (new_l != o_l) {
+              p.z[i] = (uint16_t)new_l;
+            }
           }
         }
-        const float q_l = valid ? __ldg(p.q + w_l) : 0.0f;
-        const float po_l = valid ? __ldg(p.prior + (size_t)w_l * p.layout.stride + o_l) : 0.0f;  // P_w[o]
-        int new_l = o_l;
-        const int cnt = (int)min((int64_t)32, te - base);
 
-        for (int t = 0; t < cnt; ++t) {
-          const int w = __shfl_sync(kFullMask, w_l, t);
-          const int o = __shfl_sync(kFullMask, o_l, t);
-          const float u = __shfl_sync(kFullMask, u_l, t);
-          const float qw = __shfl_sync(kFullMask, q_l, t);
-          doc_nnz += (unsigned)nnz;
-          int newt;
-          const int tile_case = nnz >> 5;  // tiles needed for nnz + 1 slots, minus one (uniform across the warp)
-          if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-          else newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
-          if (lane == t) new_l = newt;
-        }
-
-        if (valid) {
-          if (MODE == MODE_FROZEN) {
-            p.z_out[i] = new_l;
-          } else if (new_l != o_l) {
-            p.z[i] = (uint16_t)new_l;
+        if (MODE == MODE_INFER) {
+          st_nnz += doc_nnz;  // per iteration: 100 iterations of a long document overflow 32 bits
+          doc_nnz = 0;
+          const bool save = p.infer_samples == 0
+                                ? it == iters
+                                : (it > p.infer_burn_in && (it - p.infer_burn_in) % p.infer_thinning == 0);
+          if (save) {  // this warp owns document d: plain read-modify-write
+            __syncwarp();
+            int32_t* acc = p.infer_acc + (size_t)d * K;
+            for (int j = lane; j < nnz; j += 32) {
+              const uint32_t sl = slots[j];
+              acc[sl >> 16] += (int32_t)(sl & 0xffffu);
+            }
           }
         }
       }
 
-      if (MODE == MODE_UPDATE) {
+      if (MODE != MODE_FROZEN) {
         for (int j = lane; j < nnz; j += 32) p.rows[rp + j] = slots[j];
         if (lane == 0) p.row_nnz[d] = nnz;
       }
