@@ -86,7 +86,10 @@ PriorLayout make_layout(int K) {
 
 // Launch shape of the sampling kernel for one document class.
 struct SweepShape {
-  int slot_cap = 32, warps_per_cta = 8, ctas = 0, doc_chunk = 4;
+  int slot_cap = 95;   // longest row (min(K, document length)) the class holds
+  int rc = 0;          // kernel instance (sweep_kernel.cuh: ROWCLASS)
+  int cap_tiles = 0;   // wide class: tiles of the shared-memory row
+  int warps_per_cta = 8, ctas = 0, doc_chunk = 4;
   size_t smem = 0;
   bool tables_in_smem = true;
 };
@@ -131,9 +134,8 @@ struct b200lda_ctx {
   int64_t launches = 0;
 
   DeviceCorpus corp;  // training documents
-  int min_row = 64;  // narrowest row-width class
+  std::vector<SweepShape> shape_cache;  // launch shapes by (row class, tiles): computed once per context
   int class_streams = 0;  // see launch_sweep
-  bool infer_fused = true;  // b200lda_infer: all iterations of a document in one kernel visit (B200LDA_INFER_FUSED=0: one launch set per iteration)
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
@@ -250,15 +252,18 @@ int sweep_occupancy(int rc, int threads, size_t smem, int* occ) {
   switch (rc) {
     case 0: return sweep_occupancy_rc<MODE, LIVE, TS, 0>(threads, smem, occ);
     case 1: return sweep_occupancy_rc<MODE, LIVE, TS, 1>(threads, smem, occ);
-    default: return sweep_occupancy_rc<MODE, LIVE, TS, 2>(threads, smem, occ);
+    case 2: return sweep_occupancy_rc<MODE, LIVE, TS, 2>(threads, smem, occ);
+    default: return sweep_occupancy_rc<MODE, LIVE, TS, 3>(threads, smem, occ);
   }
 }
 
-// which kernel instance serves rows of this capacity (sweep_kernel.cuh: ROWCLASS)
-int rowclass_for(int slot_cap) { return slot_cap <= 64 ? 0 : slot_cap <= 128 ? 1 : 2; }
+// which kernel instance serves rows of up to this many slots (sweep_kernel.cuh: ROWCLASS)
+int rowclass_for(int max_row) {
+  for (int rc = 0; rc < kWideClass; ++rc)
+    if (max_row <= rowclass_max_len(rc)) return rc;
+  return kWideClass;
+}
 
-// Shared memory per CTA = [invden | ab] (2K floats, when they fit) + per warp [slots | prefix]
-// of slot_cap entries each.
 int occupancy_of(bool ts, int rc, int threads, size_t smem, int* out) {
   int occ[4] = {0, 0, 0, 0};
   if (ts) {
@@ -278,11 +283,21 @@ int occupancy_of(bool ts, int rc, int threads, size_t smem, int* out) {
 
 // Picks, among {tables in shared memory, tables read through L1} x {8, 4, 2, 1 warps per CTA}, the
 // shape with the most resident warps per SM (ties: shared-memory tables, then wider CTAs). At
-// K = 1000 that is smem tables at 4 CTAs x 8 warps; at K = 10 000 the 120 KB of tables would leave
-// one CTA per SM, so they stay in global memory.
-int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepShape* out) {
-  const size_t tab = 3 * sizeof(float) * (size_t)c->K;  // invden, ab, per-CTA n_k delta
-  const size_t per_warp = sweep_smem_per_warp(slot_cap);
+// K = 1000 that is smem tables at 8 warps per CTA; at K = 10 000 the 120 KB of tables would leave
+// one CTA per SM, so they stay in global memory. Shapes depend only on (K, row class, tiles), so
+// they are computed once per context (the occupancy queries cost ~10 us each, 64 per shape).
+int shape_for(b200lda_ctx* c, int max_row, int doc_chunk, int longest, SweepShape* out) {
+  const int rc = rowclass_for(max_row);
+  const int cap_tiles = rc == kWideClass ? max_row / 32 + 1 : 0;
+  for (const SweepShape& s : c->shape_cache)
+    if (s.rc == rc && s.cap_tiles == cap_tiles) {
+      *out = s;
+      out->slot_cap = max_row;
+      out->doc_chunk = doc_chunk;
+      return B200LDA_OK;
+    }
+  const size_t tab = sizeof(uint32_t) * (size_t)sweep_table_words(c->K);  // invden, ab, per-CTA n_k delta
+  const size_t per_warp = sizeof(uint32_t) * (size_t)sweep_warp_words(c->K, cap_tiles);
   SweepShape best;
   int best_warps = 0;
   for (int ts = 1; ts >= 0; --ts) {
@@ -290,11 +305,11 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
       const size_t need = (ts ? tab : 0) + per_warp * wpc;
       if (need > kMaxSmemPerCta) continue;
       int occ = 0;
-      TRY(occupancy_of(ts != 0, rowclass_for(slot_cap), wpc * 32, need, &occ));
+      TRY(occupancy_of(ts != 0, rc, wpc * 32, need, &occ));
       if (occ * wpc > best_warps) {
         best_warps = occ * wpc;
-        best.slot_cap = slot_cap;
-        best.doc_chunk = doc_chunk;
+        best.rc = rc;
+        best.cap_tiles = cap_tiles;
         best.tables_in_smem = ts != 0;
         best.warps_per_cta = wpc;
         best.smem = need;
@@ -304,22 +319,27 @@ int shape_for(b200lda_ctx* c, int slot_cap, int doc_chunk, int longest, SweepSha
   }
   if (best_warps == 0)
     return fail(B200LDA_ERANGE, "document rows of %d slots do not fit shared memory (K=%d, longest doc=%d)",
-                slot_cap, c->K, longest);
+                max_row, c->K, longest);
+  c->shape_cache.push_back(best);
   *out = best;
+  out->slot_cap = max_row;
+  out->doc_chunk = doc_chunk;
   return B200LDA_OK;
 }
 
-// Row-width classes with power-of-two slot capacities (min_row, 2 min_row, ... up to the widest
-// row): per-warp shared memory follows the row width, so the bulk of short documents leaves most
-// of the SM's 228 KB to the L1 cache and the long tail does not dictate everyone's occupancy.
+// Row-width classes: rows of up to 95 / 159 / 255 slots (min(K, document length)) live in registers
+// (3 / 5 / 8 tiles, one kernel instance each so the narrow classes keep their register allocation);
+// longer rows live in shared memory, in classes of 511, 1023, ... slots up to the widest row, so
+// the long tail does not dictate everyone's shared memory and occupancy.
 // len_ge[L] = number of documents with at least L tokens (documents are ordered longest first).
 int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>& len_ge) {
   cp.classes.clear();
   cp.tune_waits = 8;
   if (c->timed_corpus == &cp) c->timed_corpus = nullptr;  // the classes the pending timings describe are gone
-  const int widest = std::max(32, round_up32(std::min(c->K, std::max(1, cp.max_doc_len))));
+  const int widest = std::min(c->K, std::max(1, cp.max_doc_len));
   std::vector<int> caps;
-  for (int cap = c->min_row; cap < widest; cap *= 2) caps.push_back(cap);
+  for (int rc = 0; rc < kWideClass && rowclass_max_len(rc) < widest; ++rc) caps.push_back(rowclass_max_len(rc));
+  for (int cap = 511; cap < widest; cap = 2 * cap + 1) caps.push_back(cap);
   caps.push_back(widest);
   auto docs_with_row_above = [&](int cap) -> int64_t {  // rows are min(len, K) slots wide
     if (cap >= c->K || cap + 1 >= (int)len_ge.size()) return 0;
@@ -339,7 +359,7 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
     dc.end = i == 0 ? cp.D : docs_with_row_above(caps[i - 1]);
     if (dc.end <= dc.begin) continue;
     dc.tokens = (i == 0 ? all_tokens : tokens_with_row_above(caps[i - 1])) - tokens_with_row_above(caps[i]);
-    TRY(shape_for(c, caps[i], caps[i] > 256 ? 1 : 4, cp.max_doc_len, &dc.shape));
+    TRY(shape_for(c, caps[i], caps[i] > 255 ? 1 : 4, cp.max_doc_len, &dc.shape));
     cp.classes.push_back(dc);
   }
   // Background classes. A class with too few documents to keep every resident warp busy several
@@ -523,8 +543,8 @@ int build_doc_rows(b200lda_ctx* c, DeviceCorpus& cp) {
   } else {
     const size_t need = sizeof(uint32_t) * (size_t)c->K * wpc * grid;
     if (need > c->hist_scratch_bytes) {
+      if (c->d_hist_scratch) c->device_bytes -= (int64_t)c->hist_scratch_bytes;
       dev_free(c->d_hist_scratch);
-  dev_free(c->d_hyper);
       TRY(dev_alloc(c, reinterpret_cast<void**>(&c->d_hist_scratch), need));
       c->hist_scratch_bytes = need;
     }
@@ -570,7 +590,6 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
   p.uniforms = nullptr;
   p.layout = c->layout;
   p.K = c->K;
-  p.exclude_self = 1;
   p.beta_f = (float)c->beta;
   p.seed = c->cfg.seed;
   p.sweep = sweep;
@@ -586,7 +605,7 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
-  p.slot_cap = sh.slot_cap;
+  p.cap_tiles = sh.cap_tiles;
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
   const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
@@ -595,13 +614,15 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
       1, std::min<int64_t>(grid_cap, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
   const int threads = sh.warps_per_cta * 32;
 #define B200LDA_LAUNCH(TS, RC) k_gibbs_sweep<MODE, LIVE, TS, RC><<<ctas, threads, sh.smem, stream>>>(p)
-  switch (rowclass_for(sh.slot_cap) * 2 + (sh.tables_in_smem ? 1 : 0)) {
+  switch (sh.rc * 2 + (sh.tables_in_smem ? 1 : 0)) {
     case 0: B200LDA_LAUNCH(false, 0); break;
     case 1: B200LDA_LAUNCH(true, 0); break;
     case 2: B200LDA_LAUNCH(false, 1); break;
     case 3: B200LDA_LAUNCH(true, 1); break;
     case 4: B200LDA_LAUNCH(false, 2); break;
-    default: B200LDA_LAUNCH(true, 2); break;
+    case 5: B200LDA_LAUNCH(true, 2); break;
+    case 6: B200LDA_LAUNCH(false, 3); break;
+    default: B200LDA_LAUNCH(true, 3); break;
   }
 #undef B200LDA_LAUNCH
   c->launches += 1;
@@ -657,7 +678,7 @@ void retune_background(b200lda_ctx* c, DeviceCorpus& cp) {
 template <int MODE, bool LIVE>
 int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p) {
   retune_background(c, cp);
-  CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+  if (MODE != MODE_INFER) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
   CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
@@ -784,12 +805,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->beta = cfg->beta;
   c->sm_count = prop.multiProcessorCount;
   c->layout = make_layout(c->K);
-  if (const char* e = std::getenv("B200LDA_MIN_ROW")) {  // tuning knob for experiments
-    const int v = atoi(e);
-    if (v >= 32) c->min_row = round_up32(v);
-  }
   if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
-  if (const char* e = std::getenv("B200LDA_INFER_FUSED")) c->infer_fused = atoi(e) != 0;
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {
@@ -1089,13 +1105,12 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
   int samples = 0;
   for (int32_t it = 1; it <= iterations; ++it)
     if (it > burn_in && (it - burn_in) % thinning == 0) ++samples;
-  if (c->infer_fused && iterations >= 1) {
+  if (iterations >= 1) {
     // n_wk / n_k are frozen, so every document is an independent chain: one launch set in which a
-    // warp runs all iterations of its document (row resident in shared memory, samples added to
-    // d_acc as they are reached) replaces `iterations` launch sets + accumulate passes. Same
-    // Philox keys (sweep = iteration), so the result is the per-iteration schedule's, bit for bit.
-    SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, 0u);
-    p.exclude_self = 0;  // the held-out tokens are not part of n_wk / n_k
+    // warp runs all iterations of its document (samples added to d_acc as they are reached)
+    // replaces `iterations` launch sets + accumulate passes. Philox keys: sweep = iteration.
+    SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, 0u);  // MODE_INFER: the held-out tokens are not part of n_wk / n_k
+    p.stats = c->d_counters + 9;  // inference leaves the training chain's sweep statistics alone
     p.stats_cum = c->d_counters + 9;
     p.seed = seed;
     p.global_tok_off = 0;
@@ -1106,25 +1121,10 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
     p.infer_acc = d_acc;
     if ((rc = launch_sweep<MODE_INFER, false>(c, cp, p))) return cleanup(rc);
     if (samples == 0) samples = 1;  // Mallet: no sample saved -> the final state (added by the kernel)
-  } else {
-    for (int32_t it = 1; it <= iterations; ++it) {
-      SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, (uint32_t)it);
-      p.exclude_self = 0;
-      p.stats_cum = c->d_counters + 9;
-      p.seed = seed;
-      p.global_tok_off = 0;
-      if ((rc = launch_sweep<MODE_UPDATE, false>(c, cp, p))) return cleanup(rc);
-      if (it > burn_in && (it - burn_in) % thinning == 0) {
-        k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr,
-                                                                               cp.d_row_nnz, cp.d_rows, d_acc);
-        c->launches += 1;
-      }
-    }
-    if (samples == 0) {  // Mallet: no sample saved -> use the final state
-      k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
-                                                                             cp.d_rows, d_acc);
-      samples = 1;
-    }
+  } else {  // no iterations at all: the (random) initial state is the sample
+    k_infer_accumulate<<<grid_for(c, num_docs * 32, 256), 256, 0, c->stream>>>(num_docs, c->K, cp.d_row_ptr, cp.d_row_nnz,
+                                                                           cp.d_rows, d_acc);
+    samples = 1;
   }
   k_infer_theta<<<grid_for(c, (int64_t)DK, 256), 256, 0, c->stream>>>(num_docs, c->K, samples, cp.d_doc_ptr, d_acc, c->d_alpha,
                                                                      c->alpha_sum, d_theta);

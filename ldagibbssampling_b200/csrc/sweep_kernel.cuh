@@ -3,33 +3,35 @@
 // Replaces cc.mallet.topics.WorkerRunnable.sampleTopicsForOneDoc, reached through
 // model.estimate() at reference cmu_ron/TrainAndPredict.java:166 and cmu/TrainAndPredict.java:265
 // (SURVEY.md §8 rows a4, a5). It is NOT a translation of SparseLDA's s/r/q walk over packed rows:
-//   * a warp owns a document; the document's sparse topic row (topic<<16 | count, ascending
-//     topic) lives in shared memory and is the only state that changes token to token;
-//   * doc bucket: lane j holds non-zero topic j, gathers n_wk[w, topic_j] (4 B each),
-//     forms  n_dk (n_wk + beta) / (n_k + V beta)  and the warp scans it (shuffle prefix sum);
+//   * a warp owns a document for one visit; the document's sparse topic row lives in REGISTERS for
+//     the whole visit: nt tiles of 32 slots, lane l holds slot (g, l) of every tile g as
+//     (topic << 16 | count) plus the cached weight  wt = invden[topic] * count.  Slots never shift:
+//     a topic that leaves the document kills its slot in place, a topic that enters it takes a dead
+//     slot of its preferred tile (tiles are topic ranges fixed at visit start, so a tile's 32 n_wk
+//     gathers stay on few 128-byte lines). A token step therefore edits at most two slots, each by
+//     the lane that owns it: no shared-memory row, no shuffles, no shifting;
+//   * doc bucket: every lane gathers n_wk[w, topic] for its slots (4 B each), forms
+//     (n_wk + beta) * wt, sums its own slots and ONE warp scan runs over the 32 lane totals
+//     (lane-strided prefix); the bucket search is a per-lane count plus one ballot;
 //   * prior bucket: alpha_k (n_wk + beta) / (n_k + V beta) is word-only, so its mass and prefix
 //     table are built once per sweep per word (table_kernels.cuh); a draw that lands there is
-//     resolved by a fan-out-32 search = one coalesced 128-byte line per level, and the loads that
-//     depend only on the token (P_w[o], the top level) are requested before the bucket is known;
-//   * randomness: Philox keyed by (seed; global token, sweep), 32 tokens per warp batch, one
-//     lane each, so the RNG costs ~2 instructions per token;
-//   * count moves: the row edit happens in shared memory (two count updates, a one-slot shift only
-//     when a topic enters or leaves the document), integer RED atomics carry the n_wk / n_k moves.
-// The kernel is limited by instruction issue (72-77 % of issue slots) with L1TEX second
-// (profiles/r01_sweep_v7_ncu_summary.txt, profiles/r01_tuning.md), so the token step is specialised
-// on the number of 32-slot tiles of the row: token_step_tiles<NT> is straight-line code (rows
-// zero-padded to whole tiles so nothing is predicated per lane, prefixes in registers, no inner
-// loops); token_step_generic keeps the loop form for rows wider than kRegTiles tiles. Slots stay in
-// tile order (lane = slot mod 32) on purpose: 32 consecutive sorted topics per gather instruction
-// touch ~13 of the word row's 32 lines, a lane-blocked order touches 32 and is L1TEX-bound.
-// Documents are visited through doc_order (longest first); the host launches the kernel once per
-// row-width class so that per-warp shared memory follows the row width.
+//     resolved by a fan-out-32 search = one coalesced 128-byte line per level;
+//   * the 32 tokens of a batch are fetched one per lane (word, old topic, Philox draw, Q_w, P_w[o],
+//     invden[o], ab[o]) and staged in shared memory, so a token step starts with two broadcast
+//     128-bit shared loads instead of a shuffle per field;
+//   * count moves: integer RED atomics carry the n_wk moves, n_k moves are accumulated per CTA;
+//   * visit end: the live slots go back to the packed row in ascending topic order through a
+//     K-bit bitmap in shared memory (rank = popcount of the lower bits).
+// token_step<NT> is straight-line code specialised on the tile count (NT = 1..8); rows that can
+// exceed 8 tiles (documents with more than 255 tokens when K > 255) run token_step_wide, the same
+// algorithm with the row in shared memory and loops over tiles.
 // MODE_UPDATE serves LIVE (LIVE=true: n_wk read through L1/L2 and written in place) and DEFERRED
 // (LIVE=false: frozen n_wk through the read-only path, moves go to a second buffer);
 // MODE_FROZEN moves nothing (north-star parity mode). MODE_INFER is held-out inference
-// (TopicInferencer.getSampledDistribution): n_wk / n_k are frozen, so documents are independent
-// chains and a warp runs ALL iterations of its document in one visit, the row staying in shared
-// memory, adding the row to the document's sample accumulator at every saved iteration.
+// (TopicInferencer.getSampledDistribution): n_wk / n_k are frozen and do not contain the
+// document, so documents are independent chains and a warp runs ALL iterations of its document in
+// one kernel visit (one row visit per iteration), adding the row to the document's sample
+// accumulator at every saved iteration.
 #pragma once
 #include "device_common.cuh"
 
@@ -57,10 +59,8 @@ struct SweepParams {
   const float* uniforms;      // [N] or nullptr (Philox)
   PriorLayout layout;
   int K;
-  int slot_cap;               // shared-memory slots per warp (multiple of 32)
+  int cap_tiles;              // wide class: tiles of the shared-memory row (0 in the register classes)
   int doc_chunk;              // documents fetched per scheduler atomic (strided through doc_order)
-  int exclude_self;           // 1: the token being resampled is counted in n_wk (training);
-                              // 0: held-out inference against frozen counts (TopicInferencer)
   float beta_f;
   uint64_t seed;
   uint32_t sweep;
@@ -76,34 +76,51 @@ struct SweepParams {
 };
 
 #ifndef B200LDA_SWEEP_GROUP
-#define B200LDA_SWEEP_GROUP 4  // measured on B200: 4 > 3 > 2 > 1 (profiles/r01_tuning.md)
+#define B200LDA_SWEEP_GROUP 4  // wide path: tiles whose gathers are in flight together
 #endif
-constexpr int kGroup = B200LDA_SWEEP_GROUP;  // generic path: tiles whose gathers are in flight together
-#ifndef B200LDA_REG_TILES
-#define B200LDA_REG_TILES 8  // measured: C3 (rows ~150 slots) 1.11 -> 1.41 Gtok/s, C4 unchanged
-#endif
-constexpr int kRegTiles = B200LDA_REG_TILES;  // rows of up to this many tiles take the straight-line register path
+constexpr int kGroup = B200LDA_SWEEP_GROUP;
 
-// Shared memory per warp: slot_cap x {uint32 row slot, float prefix} = 8 bytes per slot, plus
-// kRowPad zeroed spare slots behind the row (the register path reads whole tiles).
-constexpr int kSmemBytesPerSlot = 8;
-constexpr int kRowPad = 32;
-__host__ __device__ constexpr size_t sweep_smem_per_warp(int slot_cap) {
-  return (size_t)kSmemBytesPerSlot * (size_t)slot_cap + sizeof(uint32_t) * kRowPad;
-}
+// ROWCLASS selects the token-step variants a kernel instance carries, so that the register
+// allocation (one per kernel) of the narrow classes is not dictated by the 8-tile variant:
+//   0: documents of <= 95 tokens (NT <= 3)   1: <= 159 (NT <= 5)   2: <= 255 (NT <= 8)
+//   3: longer documents: row in shared memory, loops over tiles (token_step_wide)
+// A row of n live slots starts a visit with n/32 + 1 tiles and grows a tile only when all of its
+// slots are live, so a document of L tokens (at most min(K, L) topics) never needs more than
+// min(K, L)/32 + 1 tiles.
+constexpr int kRowClasses = 4;
+constexpr int kWideClass = 3;
+__host__ __device__ constexpr int rowclass_max_tiles(int rc) { return rc == 0 ? 3 : rc == 1 ? 5 : rc == 2 ? 8 : 0; }
+__host__ __device__ constexpr int rowclass_max_len(int rc) { return 32 * rowclass_max_tiles(rc) - 1; }
 
 #ifndef B200LDA_TOP_EARLY_NT
 #define B200LDA_TOP_EARLY_NT 3  // rows of up to this many tiles request the prior's top level at the start of the token step
 #endif
-#ifndef B200LDA_SWEEP_MIN_CTAS
-#define B200LDA_SWEEP_MIN_CTAS 4   // 8-warp CTAs per SM the register allocation must allow
+#ifndef B200LDA_RC0_MIN_CTAS
+#define B200LDA_RC0_MIN_CTAS 5
 #endif
-#ifndef B200LDA_ROWCLASS0_MIN_CTAS
-#define B200LDA_ROWCLASS0_MIN_CTAS 4
+#ifndef B200LDA_RC1_MIN_CTAS
+#define B200LDA_RC1_MIN_CTAS 4
 #endif
-#ifndef B200LDA_ROWCLASS1_MIN_CTAS
-#define B200LDA_ROWCLASS1_MIN_CTAS 4
+#ifndef B200LDA_RC2_MIN_CTAS
+#define B200LDA_RC2_MIN_CTAS 4
 #endif
+#ifndef B200LDA_RC3_MIN_CTAS
+#define B200LDA_RC3_MIN_CTAS 4
+#endif
+__host__ __device__ constexpr int rowclass_min_ctas(int rc) {
+  return rc == 0 ? B200LDA_RC0_MIN_CTAS : rc == 1 ? B200LDA_RC1_MIN_CTAS : rc == 2 ? B200LDA_RC2_MIN_CTAS : B200LDA_RC3_MIN_CTAS;
+}
+
+// Shared memory (32-bit words). Per CTA: [invden | ab | n_k delta] (3K, rounded to 4, when
+// TABLES_IN_SMEM). Per warp: the token batch (32 tokens x 8 words), the write-back bitmap and its
+// word prefix (2 x ceil(K/32)), and in the wide class the row: slots, weights, lane-local
+// prefixes (32 cap_tiles each) and the tile bounds (cap_tiles).
+constexpr int kBatchWords = 256;
+__host__ __device__ constexpr int bitmap_words(int K) { return (K + 31) >> 5; }
+__host__ __device__ constexpr int sweep_table_words(int K) { return (3 * K + 3) & ~3; }
+__host__ __device__ constexpr int sweep_warp_words(int K, int cap_tiles) {
+  return (kBatchWords + 2 * bitmap_words(K) + 97 * cap_tiles + 3) & ~3;
+}
 
 // The kernel's dynamic shared memory, addressed by WORD OFFSET everywhere: indexing the extern
 // array keeps every access a plain LDS/STS/ATOMS with an immediate base, whereas pointers carried in
@@ -112,6 +129,31 @@ extern __shared__ __align__(16) unsigned char b200lda_smem_raw[];
 __device__ __forceinline__ uint32_t& smem_u32(int word) { return reinterpret_cast<uint32_t*>(b200lda_smem_raw)[word]; }
 __device__ __forceinline__ float& smem_f32(int word) { return reinterpret_cast<float*>(b200lda_smem_raw)[word]; }
 __device__ __forceinline__ int* smem_i32_ptr(int word) { return reinterpret_cast<int*>(b200lda_smem_raw) + word; }
+__device__ __forceinline__ uint32_t* smem_u32_ptr(int word) { return reinterpret_cast<uint32_t*>(b200lda_smem_raw) + word; }
+__device__ __forceinline__ uint4& smem_u128(int word) { return reinterpret_cast<uint4*>(b200lda_smem_raw)[word >> 2]; }
+
+// Shared-memory accesses of the token step go through the 32-bit shared-window address kept in a
+// register (WarpCtx::sbase / batch_addr): left to itself the compiler rematerialises the window base
+// (S2R CgaCtaId, ULEA) and the per-warp offset arithmetic at every use (~20 instructions per token
+// in the first register-path build, profiles/r02_tuning.md).
+__device__ __forceinline__ uint32_t smem_window_addr() {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(b200lda_smem_raw);
+  asm volatile("" : "+r"(a));  // opaque: keep it in a register
+  return a;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void reds_add_i32(uint32_t addr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 #ifndef B200LDA_LIVE_L1
 #define B200LDA_LIVE_L1 1
@@ -123,7 +165,9 @@ __device__ __forceinline__ int* smem_i32_ptr(int word) { return reinterpret_cast
 // launch, so nothing is older than the sweep. LIVE is racy across documents by design; what the L1
 // path buys is the hot words' rows at small K (C2, K = 100: 40.1 -> 24.8 ms per sweep).
 // B200LDA_LIVE_L1=0 reads at L2 (ld.global.cg), the point of coherence of the atomics.
-__device__ __forceinline__ int live_load(const int32_t* cell) {
+template <bool LIVE>
+__device__ __forceinline__ int count_load(const int32_t* cell) {
+  if (!LIVE) return __ldg(cell);
 #if B200LDA_LIVE_L1
   return __ldca(cell);
 #else
@@ -135,15 +179,20 @@ __device__ __forceinline__ int live_load(const int32_t* cell) {
 struct WarpCtx {
   int lane;
   float beta_f;
-  int excl;
   int K;
   // word offsets into the kernel's shared memory
-  int slots;   // this warp's row
-  int pref;    // this warp's prefix scratch (generic path)
   int tab;     // [invden | ab | n_k delta] (TABLES_IN_SMEM): invden at tab, ab at tab + K, deltas at tab + 2K
+  int batch;   // this warp's token batch
+  int bm;      // write-back bitmap, pf = bm + bmw: exclusive popcount prefix per bitmap word
+  int bmw;
+  int row;     // wide class: slots at row, weights at row + 32 capT, prefixes at row + 64 capT, bounds at row + 96 capT
+  int capT;
   bool nkd_in_smem;
   int top_lane;  // offset of this lane's entry of the top search level inside a word's prior block, -1: none
   unsigned st_moved, st_prior;
+  uint32_t sbase;       // shared-window address of word 0 of the kernel's shared memory
+  uint32_t batch_addr;  // shared-window address of this warp's token batch
+  uint32_t row_bytes;   // 4 K: bytes of one n_wk row
 };
 
 // Prior bucket: skip the own-token mass delta at topic o, then the fan-out-32 search.
@@ -205,313 +254,342 @@ __device__ __forceinline__ void count_moves(const SweepParams& p, const WarpCtx&
   }
 }
 
-// ---- register path: rows that fit NT tiles with room for one more slot (nnz + 1 <= 32 NT) -------
-// The warp's row in shared memory is ZERO-PADDED past nnz up to 32 NT slots (kRowPad spare slots
-// behind slot_cap): a padded slot reads topic 0 / count 0, weighs exactly +0 and can never be the
-// old topic's slot, so loads, weights and the bucket search carry no per-lane validity predicate.
-// Prefixes stay in registers; the row edit happens in shared memory.
-template <int NT, int MODE, bool LIVE, bool TS, int TE>
-__device__ __forceinline__ int token_step_tiles(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
-                                                float qw, float po_l, int t) {
+__device__ __forceinline__ int warp_scan_inclusive_i32(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(kFullMask, v, d);
+    if (lane >= d) v += y;
+  }
+  return v;
+}
+
+// Visit-start split of a packed row of n slots over nt = n/32 + 1 tiles: tile g takes
+// q + [g < r] consecutive sorted positions starting at g q + min(g, r)  (q = n / nt, r = n % nt).
+struct RowSplit {
+  int q, r;
+  __device__ __forceinline__ int begin(int g) const { return g * q + min(g, r); }
+  __device__ __forceinline__ int size(int g) const { return q + (g < r ? 1 : 0); }
+};
+__device__ __forceinline__ RowSplit row_split(int n, int nt) {
+  RowSplit s;
+  s.q = n / nt;
+  s.r = n - s.q * nt;
+  return s;
+}
+
+// Write-back bitmap, step 2 and 3 (after every live slot has set its topic's bit): exclusive
+// popcount prefix per bitmap word; returns the number of live slots.
+__device__ __forceinline__ int bitmap_prefix(const WarpCtx& c) {
+  int running = 0;
+  for (int base = 0; base < c.bmw; base += 32) {
+    const int j = base + c.lane;
+    const int cnt = j < c.bmw ? __popc(smem_u32(c.bm + j)) : 0;
+    const int incl = warp_scan_inclusive_i32(cnt, c.lane);
+    if (j < c.bmw) smem_u32(c.bm + c.bmw + j) = (uint32_t)(running + incl - cnt);
+    running += __shfl_sync(kFullMask, incl, 31);
+  }
+  return running;
+}
+__device__ __forceinline__ int bitmap_rank(const WarpCtx& c, int topic) {
+  const int wd = topic >> 5;
+  return (int)smem_u32(c.bm + c.bmw + wd) + __popc(smem_u32(c.bm + wd) & ((1u << (topic & 31)) - 1u));
+}
+
+// ---- register path ------------------------------------------------------------------------------
+// sv / wt hold MAXNT tiles; tiles at or beyond nt are all-dead (0 / +0). NT == nt.
+// nv holds the n_wk counts of THIS token's word at the row's topics, requested one token ago; the
+// step requests the next token's counts from the row as it stands (before this token's move is
+// known) and leaves them in nv: a move changes the row's topic set in at most one slot, which is
+// re-gathered by the lane that takes it. The gather latency is thereby off the token-to-token
+// dependent chain. In LIVE mode the request precedes this token's own count moves, so when the
+// next token is of the same word the two affected counts are fixed up in registers.
+// Branch conditions that are warp-uniform by construction (bucket, moved, new-to-row) go through
+// votes: the compiler then emits uniform branches without divergence bookkeeping around the warp
+// collectives inside.
+template <int NT, int MAXNT, int MODE, bool LIVE, bool TS, int TE>
+__device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint32_t (&sv)[MAXNT], float (&wt)[MAXNT],
+                                          int (&nv)[MAXNT], int& nt, int bnd, uint32_t tok_addr) {
+  constexpr bool EXCL = MODE != MODE_INFER;
   const int lane = c.lane;
-  const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
+  const uint4 ta = lds_u128(tok_addr);       // word, old topic, uniform, Q_w
+  const uint4 tb = lds_u128(tok_addr + 16);  // invden[o], ab[o] (0 in inference), P_w[o], next token's word
+  const int w = (int)ta.x, o = (int)ta.y;
+  const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
+  const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
+  const char* nwk_bytes = reinterpret_cast<const char*>(p.nwk_read);
+  const char* nrow_next = nwk_bytes + (size_t)tb.w * (size_t)c.row_bytes;
+  asm volatile("" : "+l"(nrow_next));  // opaque: per-gather address = one IMAD.WIDE off this pointer
+  int nvn[NT];
+#pragma unroll
+  for (int g = 0; g < NT; ++g)  // a dead slot reads a valid cell; its weight is +0
+    nvn[g] = count_load<LIVE>(reinterpret_cast<const int32_t*>(nrow_next + ((size_t)(sv[g] >> 16) << 2)));
   constexpr bool kTopEarly = NT <= TE;  // request the prior's top level before the bucket is known
   float vtop = 0.0f;
   if (kTopEarly) vtop = prior_top_entry(p, c, w);
-  uint32_t sv[NT];
-  int nv[NT];
-#pragma unroll
-  for (int g = 0; g < NT; ++g) {
-    sv[g] = smem_u32(c.slots + (g << 5) + lane);
-    const int32_t* cell = nrow + (sv[g] >> 16);  // padded slots read n_wk[w, 0]: harmless, weight is 0
-    nv[g] = LIVE ? live_load(cell) : __ldg(cell);
-  }
   // a live slot of topic o reads (o << 16) + count with 1 <= count <= 0xffff
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
   // Lane-strided prefix: the lane sums its own slots tile by tile (from +0), ONE warp scan runs over
   // the 32 lane totals, slot (g, lane) gets P = E_lane + s[g]. The cumulative order is lane-major.
   float s[NT];
   float run = 0.0f;
-  int myjo = -1;
 #pragma unroll
   for (int g = 0; g < NT; ++g) {
-    const int topic = (int)(sv[g] >> 16);
     const bool is_old = (sv[g] - okey) < 0xffffu;
-    if (is_old) myjo = (g << 5) + lane;
-    const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
-    const int n = max(nv[g] - ((int)is_old & c.excl), 0);
-    const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
-    const float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
-    run = fadd(run, a);
+    int n = nv[g];
+    if (EXCL && is_old) n -= 1;
+    n = max(n, 0);
+    const float wv = is_old ? fsub(wt[g], inv_o) : wt[g];
+    run = fadd(run, fmul(fadd((float)n, c.beta_f), wv));
     s[g] = run;
   }
   const float incl = warp_scan_inclusive(run, lane);
   const float E = shfl_up1_or_zero(incl);
   const float A = __shfl_sync(kFullMask, incl, 31);
-  const int jo = __reduce_max_sync(kFullMask, myjo);
-  float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
-  delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
   qp = qp < 0.0f ? 0.0f : qp;
   const float x = fmul(u, fadd(A, qp));
 
-  int newt;
-  int jn = -1;  // slot of newt when it already has one
-  if (x < A) {
+  int newt = o;
+  const bool doc_bucket = __any_sync(kFullMask, x < A);
+  if (doc_bucket) {
     // First slot in cumulative (lane-major) order whose prefix exceeds x: the lowest lane with a
-    // hit and, prefixes being non-decreasing inside a lane, its count of non-hits. A padded slot
-    // repeats the prefix of the lane's slot before it, so it is never a lane's first hit unless the
-    // lane holds no slot of the row at all (the j < nnz test). No hit (x within an ulp of A): last slot.
+    // hit and, prefixes being non-decreasing inside a lane, its count of non-hits. Within an ulp of
+    // a lane boundary that slot can be one that adds no weight (dead, or the token's own slot when
+    // the token is its only one), or there is none at all: the token then keeps its topic.
     int cnt = 0;
 #pragma unroll
     for (int g = 0; g < NT; ++g) cnt += (fadd(E, s[g]) > x) ? 0 : 1;
-    const int jc = (cnt << 5) + lane;
-    const unsigned b = __ballot_sync(kFullMask, (cnt < NT) && (jc < nnz));
-    jn = b ? __shfl_sync(kFullMask, jc, __ffs(b) - 1) : nnz - 1;
-    newt = (int)(smem_u32(c.slots + jn) >> 16);  // shared memory still holds the row as loaded
+    const unsigned b = __ballot_sync(kFullMask, cnt < NT);
+    uint32_t mine = sv[0];
+#pragma unroll
+    for (int g = 1; g < NT; ++g) mine = (cnt == g) ? sv[g] : mine;
+    const uint32_t pk = __shfl_sync(kFullMask, mine, __ffs(b) - 1);  // b == 0: lane 31's slot, rejected below unless valid... (see guard)
+    if (b != 0u && (pk & 0xffffu) != 0u && pk != okey) newt = (int)(pk >> 16);
   } else {
     ++c.st_prior;
     if (!kTopEarly) vtop = prior_top_entry(p, c, w);
-    newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, vtop);
+    newt = prior_search(p, lane, c.K, w, __uint_as_float(tb.z), fsub(x, A), delta, vtop);
   }
 
-  if (MODE != MODE_FROZEN && newt != o) {
+  if (MODE != MODE_FROZEN && __any_sync(kFullMask, newt != o)) {
     ++c.st_moved;
-    int pos = 0;  // #slots with topic < newt (old slot still present); only needed when newt is new to the row
-    if (jn < 0) {
-      // packed compares that a padded slot (0) fails: live slot of topic < newt, live slot of topic == newt
-      const uint32_t nkey = (uint32_t)newt << 16;
-      int less = 0, eqj = -1;
+    const float inv_n = TS ? lds_f32(c.sbase + ((uint32_t)newt << 2)) : __ldg(p.invden + newt);
+    const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
+    const bool same_word = LIVE && (int)tb.w == w;
+    // Each lane edits its own slots: -1 at the old topic's slot (it dies in place at count 0),
+    // +1 at the new topic's slot when the document already has it.
+    bool has_new = false;
 #pragma unroll
-      for (int g = 0; g < NT; ++g) {
-        less += ((sv[g] - 1u) < nkey) ? 1 : 0;
-        if ((sv[g] - nkey - 1u) < 0xffffu) eqj = (g << 5) + lane;
+    for (int g = 0; g < NT; ++g) {
+      const bool io = (sv[g] - okey) < 0xffffu;
+      const bool in = (sv[g] - nkey) < 0xffffu;
+      if (io | in) {
+        sv[g] += in ? 1u : 0xffffffffu;
+        wt[g] = fmul(in ? inv_n : inv_o, (float)(sv[g] & 0xffffu));
+        if (same_word) nvn[g] += in ? 1 : -1;  // the request preceded this token's own count moves
       }
-      pos = __reduce_add_sync(kFullMask, less);
-      jn = __reduce_max_sync(kFullMask, eqj);
+      has_new = has_new || in;
     }
-    // the old slot's count decides whether the slot disappears
-    const bool del = (smem_u32(c.slots + jo) & 0xffffu) == 1u;
-    __syncwarp();  // every lane has read the row before any lane rewrites it
-    // The edit happens in shared memory: two single-lane count updates, then (only when a slot
-    // appears or disappears) a one-slot shift of [lo, lo + width] read as a whole before it is
-    // written back. Measured against editing the register copy with shuffles: fewer instructions
-    // per tile (range test + LDS + STS) and no second copy of the row in registers.
-    if (lane == 0 && jn >= 0) smem_u32(c.slots + jn) += 1u;
-    if (lane == 1 && !del) smem_u32(c.slots + jo) -= 1u;
-    if (jn < 0 || del) {
-      // destinations [lo, lo + width] take the slot at +off; ins gets the new slot (outside the range)
-      int lo = 0x7fffffff, width = 0, off = 0, ins = -1;
-      if (jn >= 0) {             // old slot empties, newt has one already: close the gap (slot nnz-1 takes the padding's 0)
-        lo = jo; width = nnz - 1 - jo; off = 1;
-      } else if (!del) {         // new slot, old one stays: open a gap at pos
-        lo = pos + 1; width = nnz - pos - 1; off = -1; ins = pos;
-      } else if (pos <= jo) {    // old slot empties, new one appears at or below it
-        lo = pos + 1; width = jo - pos - 1; off = -1; ins = pos;
-      } else {                   // ... or above it
-        lo = jo; width = pos - 2 - jo; off = 1; ins = pos - 1;
-      }
-      if (width < 0) {  // empty range: a bare replacement of the old slot
-        lo = 0x7fffffff;
-        width = 0;
-      }
-      __syncwarp();  // count updates visible
-      uint32_t mv[NT];
+    if (!doc_bucket && !__any_sync(kFullMask, has_new)) {
+      // The topic is new to the document: lowest dead lane of its preferred tile (tiles are the
+      // topic ranges fixed at visit start: bnd = first topic of tile `lane`), else of the next tile,
+      // cyclically, that has a dead slot; none anywhere: a new tile's lane 0.
+      const int gstar = __popc(__ballot_sync(kFullMask, newt >= bnd));
+      unsigned dm[NT];
 #pragma unroll
-      for (int g = 0; g < NT; ++g) {
-        const int j = (g << 5) + lane;
-        mv[g] = 0u;
-        if ((unsigned)(j - lo) <= (unsigned)width) mv[g] = smem_u32(c.slots + j + off);
-      }
-      __syncwarp();  // whole range read before any of it is overwritten
+      for (int g = 0; g < NT; ++g) dm[g] = __ballot_sync(kFullMask, (sv[g] & 0xffffu) == 0u);
+      int gsel = -1, gany = -1;
+      unsigned msel = 0u, many = 0u;
 #pragma unroll
-      for (int g = 0; g < NT; ++g) {
-        const int j = (g << 5) + lane;
-        if ((unsigned)(j - lo) <= (unsigned)width) smem_u32(c.slots + j) = mv[g];
+      for (int g = NT - 1; g >= 0; --g) {
+        if (dm[g]) {
+          gany = g;
+          many = dm[g];
+          if (g >= gstar) {
+            gsel = g;
+            msel = dm[g];
+          }
+        }
       }
-      if (lane == 0 && ins >= 0) smem_u32(c.slots + ins) = ((uint32_t)newt << 16) | 1u;
+      if (gsel < 0) {
+        gsel = gany;
+        msel = many;
+      }
+      if (NT < MAXNT && gsel < 0) {  // every slot live: append a tile (its registers are already dead slots)
+        gsel = NT;
+        msel = 1u;
+        nt = NT + 1;
+      }
+      if (lane == __ffs(msel) - 1) {
+        // the next token's count at the slot's new topic, requested before this token's +1 is issued
+        const int fresh = count_load<LIVE>(reinterpret_cast<const int32_t*>(nrow_next + ((size_t)newt << 2))) + (same_word ? 1 : 0);
+#pragma unroll
+        for (int g = 0; g < (NT < MAXNT ? NT + 1 : NT); ++g) {
+          if (g == gsel) {
+            sv[g] = nkey;
+            wt[g] = inv_n;
+            if (g < NT) nvn[g] = fresh; else nv[g < MAXNT ? g : 0] = fresh;
+          }
+        }
+      }
     }
-    nnz += (jn < 0 ? 1 : 0) - (del ? 1 : 0);
-    __syncwarp();
-    count_moves(p, c, write_row<LIVE>(p, nrow, w, c.K), o, newt);
+    // count moves: -1 at the old topic from lane 0, +1 at the new topic from lane 1
+    if (LIVE || p.nwk_write != nullptr) {
+      if (lane < 2) {
+        const int topic = lane == 0 ? o : newt;
+        const int val = lane == 0 ? -1 : 1;
+        char* wbase = LIVE ? const_cast<char*>(nwk_bytes) : reinterpret_cast<char*>(p.nwk_write);
+        atomicAdd(reinterpret_cast<int32_t*>(wbase + (size_t)w * (size_t)c.row_bytes + ((size_t)topic << 2)), val);
+        if (TS) {
+          reds_add_i32(c.sbase + 2u * c.row_bytes + ((uint32_t)topic << 2), val);
+        } else {
+          atomicAdd(p.nk_delta + topic, val);
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int g = 0; g < NT; ++g) nv[g] = nvn[g];
   return newt;
 }
 
-// Rows [a, b) move one slot up (to [a+1, b+1)); chunks from the top so nothing is overwritten.
-__device__ __forceinline__ void row_shift_up(uint32_t* slots, int a, int b, int lane) {
-  for (int hi = b - 1; hi >= a; hi -= 32) {
-    const int j = hi - lane;
-    uint32_t v = 0u;
-    if (j >= a) v = slots[j];
-    __syncwarp();
-    if (j >= a) slots[j + 1] = v;
-    __syncwarp();
-  }
-}
-// Rows [a, b) move one slot down (to [a-1, b-1)); chunks from the bottom.
-__device__ __forceinline__ void row_shift_down(uint32_t* slots, int a, int b, int lane) {
-  for (int lo = a; lo < b; lo += 32) {
-    const int j = lo + lane;
-    uint32_t v = 0u;
-    if (j < b) v = slots[j];
-    __syncwarp();
-    if (j < b) slots[j - 1] = v;
-    __syncwarp();
-  }
-}
-
-// ---- generic path: rows of any width, loop form ----------------------------------------------------
+// ---- wide path: row in shared memory, loops over tiles ---------------------------------------------
 template <int MODE, bool LIVE, bool TS>
-__device__ __forceinline__ int token_step_generic(const SweepParams& p, WarpCtx& c, int& nnz, int w, int o, float u,
-                                               float qw, float po_l, int t) {
+__device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c, int& nt, int tok) {
+  constexpr bool EXCL = MODE != MODE_INFER;
   const int lane = c.lane;
-  uint32_t* slots = &smem_u32(c.slots);
-  float* pref = &smem_f32(c.pref);
+  const int SV = c.row, WT = c.row + 32 * c.capT, PS = c.row + 64 * c.capT, BD = c.row + 96 * c.capT;
+  const uint4 ta = smem_u128(tok);
+  const int w = (int)ta.x, o = (int)ta.y;
+  const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
   const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
-  // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any is
-  // consumed, so a wide row pays one memory latency per group, not per tile. Same lane-strided
-  // prefix as the register path: pref[j] holds the lane-local inclusive sum s of slot j.
-  const int ntiles = (nnz + 31) >> 5;
+  const uint4 tb = smem_u128(tok + 4);
+  const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
+  // Tiles go in groups of kGroup: all of a group's n_wk gathers are issued before any is consumed,
+  // so a wide row pays one memory latency per group, not per tile.
   float run = 0.0f;
-  int myjo = -1;
-  for (int t0 = 0; t0 < ntiles; t0 += kGroup) {
-    uint32_t sv[kGroup];
-    int nv[kGroup];
+  for (int t0 = 0; t0 < nt; t0 += kGroup) {
+    uint32_t svg[kGroup];
+    int nvg[kGroup];
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) {
-      const int j = ((t0 + g) << 5) + lane;
-      sv[g] = 0u;
-      nv[g] = 0;
-      if (j < nnz) {
-        sv[g] = slots[j];
-        const int32_t* cell = nrow + (sv[g] >> 16);
-        nv[g] = LIVE ? live_load(cell) : __ldg(cell);
+      svg[g] = 0u;
+      nvg[g] = 0;
+      if (t0 + g < nt) {
+        svg[g] = smem_u32(SV + ((t0 + g) << 5) + lane);
+        nvg[g] = count_load<LIVE>(nrow + (svg[g] >> 16));
       }
     }
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) {
-      const int j = ((t0 + g) << 5) + lane;
-      if (j < nnz) {
-        const int topic = (int)(sv[g] >> 16);
-        const bool is_old = (sv[g] - okey) < 0xffffu;
-        if (is_old) myjo = j;
-        const int cc = (int)(sv[g] & 0xffffu) - (int)is_old;
-        const int n = max(nv[g] - ((int)is_old & c.excl), 0);
-        const float inv = TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
-        const float a = fmul(fmul(fadd((float)n, c.beta_f), inv), (float)cc);
-        run = fadd(run, a);
-        pref[j] = run;
+      if (t0 + g < nt) {
+        const int j = ((t0 + g) << 5) + lane;
+        const bool is_old = (svg[g] - okey) < 0xffffu;
+        int n = nvg[g];
+        if (EXCL && is_old) n -= 1;
+        n = max(n, 0);
+        const float wslot = smem_f32(WT + j);
+        const float wv = is_old ? fsub(wslot, inv_o) : wslot;
+        run = fadd(run, fmul(fadd((float)n, c.beta_f), wv));
+        smem_f32(PS + j) = run;
       }
     }
   }
-  __syncwarp();
   const float incl = warp_scan_inclusive(run, lane);
   const float E = shfl_up1_or_zero(incl);
   const float A = __shfl_sync(kFullMask, incl, 31);
-  const int jo = __reduce_max_sync(kFullMask, myjo);
-  float delta = TS ? smem_f32(c.tab + c.K + o) : __ldg(p.ab + o);
-  delta = c.excl ? delta : 0.0f;
   float qp = fsub(qw, delta);
   qp = qp < 0.0f ? 0.0f : qp;
   const float x = fmul(u, fadd(A, qp));
 
-  int newt;
-  int jn = -1;
-  if (x < A) {
-    jn = nnz - 1;
-    // the lane's largest prefix is at its last slot of the row, where the local sum is `run`
-    const bool hitlane = (lane < nnz) && (fadd(E, run) > x);
-    const unsigned b = __ballot_sync(kFullMask, hitlane);
+  int newt = o;
+  const bool doc_bucket = x < A;
+  if (doc_bucket) {
+    // the lane's largest prefix is at its last tile, where the local sum is `run`
+    const unsigned b = __ballot_sync(kFullMask, fadd(E, run) > x);
     if (b) {
       const int src = __ffs(b) - 1;
-      int cand = 0;
+      uint32_t pk = 0u;
       if (lane == src) {
         int j = lane;
-        while (!(fadd(E, pref[j]) > x)) j += 32;  // ends at the lane's last slot at the latest
-        cand = j;
+        while (!(fadd(E, smem_f32(PS + j)) > x)) j += 32;  // ends at the lane's last tile at the latest
+        pk = smem_u32(SV + j);
       }
-      jn = __shfl_sync(kFullMask, cand, src);
+      pk = __shfl_sync(kFullMask, pk, src);
+      if ((pk & 0xffffu) != 0u && pk != okey) newt = (int)(pk >> 16);
     }
-    newt = (int)(slots[jn] >> 16);
   } else {
     ++c.st_prior;
-    newt = prior_search(p, lane, c.K, w, __shfl_sync(kFullMask, po_l, t), fsub(x, A), delta, prior_top_entry(p, c, w));
+    newt = prior_search(p, lane, c.K, w, __uint_as_float(tb.z), fsub(x, A), delta, prior_top_entry(p, c, w));
   }
 
   if (MODE != MODE_FROZEN && newt != o) {
     ++c.st_moved;
-    // Where does newt live (or go) in the row as it stands, old slot still present?
-    int pos = 0;
-    if (jn < 0) {
-      for (int tile = 0; (tile << 5) < nnz; ++tile) {
-        const int j = (tile << 5) + lane;
-        const bool act = j < nnz;
-        const int topic = act ? (int)(slots[j] >> 16) : 0x7fffffff;
-        const unsigned less = __ballot_sync(kFullMask, topic < newt);
-        const unsigned eq = __ballot_sync(kFullMask, topic == newt);
-        pos += __popc(less);
-        if (eq) jn = (tile << 5) + __ffs(eq) - 1;
-        if (eq || less != kFullMask) break;
+    const float inv_n = TS ? smem_f32(c.tab + newt) : __ldg(p.invden + newt);
+    const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
+    bool has_new = false;
+    for (int g = 0; g < nt; ++g) {
+      const int j = (g << 5) + lane;
+      uint32_t v = smem_u32(SV + j);
+      const bool io = (v - okey) < 0xffffu;
+      const bool in = (v - nkey) < 0xffffu;
+      if (io | in) {
+        v += in ? 1u : 0xffffffffu;
+        const uint32_t cnt = v & 0xffffu;
+        smem_u32(SV + j) = v;
+        smem_f32(WT + j) = fmul(in ? inv_n : inv_o, (float)cnt);
       }
+      has_new = has_new || in;
     }
-    const uint32_t so = slots[jo];
-    const bool del = (so & 0xffffu) == 1u;
     __syncwarp();
-    if (jn >= 0) {                 // newt already has a slot: bump it
-      if (lane == 0) {
-        slots[jn] += 1u;
-        if (!del) slots[jo] = so - 1u;
+    if (!doc_bucket && !__any_sync(kFullMask, has_new)) {
+      int ge = 0;
+      for (int g = 1 + lane; g < nt; g += 32) ge += (newt >= (int)smem_u32(BD + g)) ? 1 : 0;
+      const int gstar = __reduce_add_sync(kFullMask, ge);
+      int gsel = -1;
+      unsigned msel = 0u;
+      for (int i = 0; i < nt; ++i) {
+        int g = gstar + i;
+        if (g >= nt) g -= nt;
+        const unsigned dm = __ballot_sync(kFullMask, (smem_u32(SV + (g << 5) + lane) & 0xffffu) == 0u);
+        if (dm) {
+          gsel = g;
+          msel = dm;
+          break;
+        }
       }
-      if (del) {                   // ... and close the gap the old topic leaves
+      if (gsel < 0) {  // every slot live: append an empty tile (nt < capT by the class's document lengths)
+        gsel = nt;
+        msel = 1u;
+        smem_u32(SV + (nt << 5) + lane) = 0u;
+        smem_f32(WT + (nt << 5) + lane) = 0.0f;
+        if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
+        nt += 1;
         __syncwarp();
-        row_shift_down(slots, jo + 1, nnz, lane);
-        --nnz;
-        if (lane == 0) slots[nnz] = 0u;  // keep the zero padding behind the row
       }
-    } else if (!del) {             // new slot, old one stays
-      if (lane == 0) slots[jo] = so - 1u;
+      if (lane == __ffs(msel) - 1) {
+        smem_u32(SV + (gsel << 5) + lane) = nkey;
+        smem_f32(WT + (gsel << 5) + lane) = inv_n;
+      }
       __syncwarp();
-      row_shift_up(slots, pos, nnz, lane);
-      if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
-      ++nnz;
-    } else if (pos <= jo) {        // old slot empties, new one appears below it
-      row_shift_up(slots, pos, jo, lane);
-      if (lane == 0) slots[pos] = ((uint32_t)newt << 16) | 1u;
-    } else {                       // ... or above it
-      row_shift_down(slots, jo + 1, pos, lane);
-      if (lane == 0) slots[pos - 1] = ((uint32_t)newt << 16) | 1u;
     }
-    __syncwarp();
     count_moves(p, c, write_row<LIVE>(p, nrow, w, c.K), o, newt);
   }
   return newt;
-}
-
-// ROWCLASS selects which token-step variants a kernel instance carries, so that the register
-// allocation (one per kernel) of the narrow-row classes is not dictated by the 8-tile variant:
-//   0: rows <= 64 slots  (NT <= 3)     1: rows <= 128 slots (NT <= 5)     2: any row (NT <= 8 + loop form)
-constexpr int kRowClasses = 3;
-__host__ __device__ constexpr int rowclass_max_tiles(int rc) { return rc == 0 ? 3 : rc == 1 ? 5 : 8; }
-__host__ __device__ constexpr int rowclass_min_ctas(int rc) {
-  return rc == 0 ? B200LDA_ROWCLASS0_MIN_CTAS : rc == 1 ? B200LDA_ROWCLASS1_MIN_CTAS : B200LDA_SWEEP_MIN_CTAS;
 }
 
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM, int ROWCLASS>
 __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_sweep(const SweepParams p) {
-  constexpr int MAXNT = rowclass_max_tiles(ROWCLASS);
-  // Rows up to kTE tiles request the prior's top search level at the start of the token step. The
-  // <= 128-slot classes have the register for it at any width; in the wide class it costs more
-  // than it hides beyond 3 tiles (measured: C4 +1.3 % / C3 -2 % when applied everywhere).
+  constexpr bool WIDE = ROWCLASS == kWideClass;
+  constexpr int MAXNT = WIDE ? 1 : rowclass_max_tiles(ROWCLASS);
+  // Rows up to kTE tiles request the prior's top search level at the start of the token step.
   constexpr int kTE = ROWCLASS <= 1 ? 5 : B200LDA_TOP_EARLY_NT;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
   const int K = p.K;
 
-  // shared memory (words): [invden | ab | n_k delta] (3K, when TABLES_IN_SMEM), the warps' rows, the warps' prefixes
-  const int tab_words = TABLES_IN_SMEM ? 3 * K : 0;
+  const int tab_words = TABLES_IN_SMEM ? sweep_table_words(K) : 0;
   if (TABLES_IN_SMEM) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       smem_f32(k) = p.invden[k];
@@ -523,17 +601,22 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   WarpCtx c;
   c.lane = lane;
   c.beta_f = p.beta_f;
-  c.excl = p.exclude_self;
   c.K = K;
   c.tab = 0;
-  const int row_words = p.slot_cap + kRowPad;
-  c.slots = tab_words + warp * row_words;
-  c.pref = tab_words + nwarps * row_words + warp * p.slot_cap;
+  c.bmw = bitmap_words(K);
+  c.capT = p.cap_tiles;
+  c.batch = tab_words + warp * sweep_warp_words(K, p.cap_tiles);
+  c.bm = c.batch + kBatchWords;
+  c.row = c.bm + 2 * c.bmw;
   c.nkd_in_smem = TABLES_IN_SMEM;
   c.top_lane = (lane < p.layout.size[p.layout.nlev - 1]) ? p.layout.off[p.layout.nlev - 1] + lane : -1;
   c.st_moved = 0;
   c.st_prior = 0;
-  uint32_t* slots = &smem_u32(c.slots);
+  c.sbase = smem_window_addr();
+  c.batch_addr = c.sbase + 4u * (uint32_t)c.batch;
+  asm volatile("" : "+r"(c.batch_addr));
+  c.row_bytes = 4u * (uint32_t)K;
+  const int SV = c.row, WT = c.row + 32 * c.capT, BD = c.row + 96 * c.capT;
 
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
   const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
@@ -551,18 +634,65 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
     if (ci >= nchunks) break;
 
     for (unsigned long long di = ci; di < ndocs; di += nchunks) {
-      const int64_t d = (int64_t)__ldg(p.doc_order + p.order_begin + (int64_t)di);
-      const int64_t tb = p.doc_ptr[d], te = p.doc_ptr[d + 1];
+      // the document's header, read by lane 0 and broadcast: warp-uniform for the compiler too
+      const int64_t d = (int64_t)__shfl_sync(kFullMask, __ldg(p.doc_order + p.order_begin + (int64_t)di), 0);
+      long long h_tb = 0, h_te = 0, h_rp = 0;
+      int h_nnz = 0;
+      if (lane == 0) {
+        h_tb = p.doc_ptr[d];
+        h_te = p.doc_ptr[d + 1];
+        h_rp = p.row_ptr[d];
+        h_nnz = p.row_nnz[d];
+      }
+      const int64_t tb = __shfl_sync(kFullMask, h_tb, 0), te = __shfl_sync(kFullMask, h_te, 0);
       if (te == tb) continue;
-      const int64_t rp = p.row_ptr[d];
-      int nnz = p.row_nnz[d];
-      for (int j = lane; j < row_words; j += 32) slots[j] = j < nnz ? p.rows[rp + j] : 0u;  // zero-padded
-      __syncwarp();
-      unsigned doc_nnz = 0;
+      const int64_t rp = __shfl_sync(kFullMask, h_rp, 0);
+      int nnz = __shfl_sync(kFullMask, h_nnz, 0);
+      const int nnz_start = nnz;
 
       const int iters = MODE == MODE_INFER ? p.infer_iters : 1;
       for (int it = 1; it <= iters; ++it) {
         const uint32_t sweep_key = MODE == MODE_INFER ? (uint32_t)it : p.sweep;
+
+        // ---- visit start: the packed row (ascending topics) split evenly over nnz/32 + 1 tiles
+        int nt = (nnz >> 5) + 1;
+        const RowSplit sp = row_split(nnz, nt);
+        uint32_t sv[MAXNT];
+        float wt[MAXNT];
+        int nv[MAXNT];
+        int bnd = 0x7fffffff;  // register classes: first topic of tile `lane` (1 <= lane < nt)
+        if (!WIDE) {
+#pragma unroll
+          for (int g = 0; g < MAXNT; ++g) {
+            sv[g] = 0u;
+            wt[g] = 0.0f;
+            nv[g] = 0;
+            if (g < nt && lane < sp.size(g)) {
+              sv[g] = p.rows[rp + sp.begin(g) + lane];
+              const int topic = (int)(sv[g] >> 16);
+              const float inv = TABLES_IN_SMEM ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
+              wt[g] = fmul(inv, (float)(sv[g] & 0xffffu));
+            }
+          }
+          if (lane >= 1 && lane < nt) bnd = sp.size(lane) > 0 ? (int)(p.rows[rp + sp.begin(lane)] >> 16) : K;
+        } else {
+          for (int g = 0; g < nt; ++g) {
+            uint32_t v = 0u;
+            float wv = 0.0f;
+            if (lane < sp.size(g)) {
+              v = p.rows[rp + sp.begin(g) + lane];
+              const int topic = (int)(v >> 16);
+              const float inv = TABLES_IN_SMEM ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
+              wv = fmul(inv, (float)(v & 0xffffu));
+            }
+            smem_u32(SV + (g << 5) + lane) = v;
+            smem_f32(WT + (g << 5) + lane) = wv;
+          }
+          for (int g = 1 + lane; g < nt; g += 32)
+            smem_u32(BD + g) = sp.size(g) > 0 ? (p.rows[rp + sp.begin(g)] >> 16) : (uint32_t)K;
+          __syncwarp();
+        }
+
         for (int64_t base = tb; base < te; base += 32) {
           const int64_t i = base + lane;
           const bool valid = i < te;
@@ -578,26 +708,46 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
           }
           const float q_l = valid ? __ldg(p.q + w_l) : 0.0f;
           const float po_l = valid ? __ldg(p.prior + (size_t)w_l * p.layout.stride + o_l) : 0.0f;  // P_w[o]
-          int new_l = o_l;
+          const float inv_l = TABLES_IN_SMEM ? smem_f32(c.tab + o_l) : __ldg(p.invden + o_l);
+          float dl_l = 0.0f;  // inference: nothing of the document is in the table
+          if (MODE != MODE_INFER) dl_l = TABLES_IN_SMEM ? smem_f32(c.tab + K + o_l) : __ldg(p.ab + o_l);
           const int cnt = (int)min((int64_t)32, te - base);
+          // the word whose counts the step requests for the NEXT token (its own word again at the
+          // batch's last token: a harmless extra request)
+          int wn_l = __shfl_down_sync(kFullMask, w_l, 1);
+          if (lane + 1 >= cnt) wn_l = w_l;
+          __syncwarp();  // the previous batch has been consumed
+          smem_u128(c.batch + 8 * lane) = make_uint4((uint32_t)w_l, (uint32_t)o_l, __float_as_uint(u_l), __float_as_uint(q_l));
+          smem_u128(c.batch + 8 * lane + 4) =
+              make_uint4(__float_as_uint(inv_l), __float_as_uint(dl_l), __float_as_uint(po_l), (uint32_t)wn_l);
+          __syncwarp();
+          int new_l = o_l;
+          if (!WIDE) {  // the batch's first token: nobody requested its counts
+            const int w0 = __shfl_sync(kFullMask, w_l, 0);
+            const int32_t* nrow0 = p.nwk_read + (size_t)w0 * K;
+#pragma unroll
+            for (int g = 0; g < MAXNT; ++g)
+              if (g < nt) nv[g] = count_load<LIVE>(nrow0 + (sv[g] >> 16));
+          }
 
-          for (int t = 0; t < cnt; ++t) {
-            const int w = __shfl_sync(kFullMask, w_l, t);
-            const int o = __shfl_sync(kFullMask, o_l, t);
-            const float u = __shfl_sync(kFullMask, u_l, t);
-            const float qw = __shfl_sync(kFullMask, q_l, t);
-            doc_nnz += (unsigned)nnz;
+          uint32_t tok_addr = c.batch_addr;
+          for (int t = 0; t < cnt; ++t, tok_addr += 32u) {
             int newt;
-            const int tile_case = nnz >> 5;  // tiles needed for nnz + 1 slots, minus one (uniform across the warp)
-            if (tile_case == 0) newt = token_step_tiles<1, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 1) newt = token_step_tiles<2, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 2 || MAXNT == 3) newt = token_step_tiles<3, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 3) newt = token_step_tiles<(MAXNT >= 4 ? 4 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 4 || MAXNT == 5) newt = token_step_tiles<(MAXNT >= 5 ? 5 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 5) newt = token_step_tiles<(MAXNT >= 6 ? 6 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 6) newt = token_step_tiles<(MAXNT >= 7 ? 7 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else if (tile_case == 7) newt = token_step_tiles<(MAXNT >= 8 ? 8 : 1), MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, nnz, w, o, u, qw, po_l, t);
-            else newt = token_step_generic<MODE, LIVE, TABLES_IN_SMEM>(p, c, nnz, w, o, u, qw, po_l, t);
+            if (WIDE) {
+              newt = token_step_wide<MODE, LIVE, TABLES_IN_SMEM>(p, c, nt, c.batch + 8 * t);
+            } else {
+              // nt is uniform across the warp; instantiations beyond the class's widest row are not generated
+#define B200LDA_STEP(N) token_step<(N <= MAXNT ? N : 1), MAXNT, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, sv, wt, nv, nt, bnd, tok_addr)
+              if (nt == 1) newt = B200LDA_STEP(1);
+              else if (nt == 2) newt = B200LDA_STEP(2);
+              else if (nt == 3 || MAXNT == 3) newt = B200LDA_STEP(3);
+              else if (nt == 4) newt = B200LDA_STEP(4);
+              else if (nt == 5 || MAXNT == 5) newt = B200LDA_STEP(5);
+              else if (nt == 6) newt = B200LDA_STEP(6);
+              else if (nt == 7) newt = B200LDA_STEP(7);
+              else newt = B200LDA_STEP(8);
+#undef B200LDA_STEP
+            }
             if (lane == t) new_l = newt;
           }
 
@@ -610,33 +760,55 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
           }
         }
 
-        if (MODE == MODE_INFER) {
-          st_nnz += doc_nnz;  // per iteration: 100 iterations of a long document overflow 32 bits
-          doc_nnz = 0;
-          const bool save = p.infer_samples == 0
-                                ? it == iters
-                                : (it > p.infer_burn_in && (it - p.infer_burn_in) % p.infer_thinning == 0);
-          if (save) {  // this warp owns document d: plain read-modify-write
-            __syncwarp();
-            int32_t* acc = p.infer_acc + (size_t)d * K;
-            for (int j = lane; j < nnz; j += 32) {
-              const uint32_t sl = slots[j];
-              acc[sl >> 16] += (int32_t)(sl & 0xffffu);
+        // ---- visit end: live slots back to the packed row in ascending topic order
+        if (MODE != MODE_FROZEN) {
+          for (int j = lane; j < c.bmw; j += 32) smem_u32(c.bm + j) = 0u;
+          __syncwarp();
+          if (!WIDE) {
+#pragma unroll
+            for (int g = 0; g < MAXNT; ++g)
+              if (sv[g] & 0xffffu) atomicOr(smem_u32_ptr(c.bm + (sv[g] >> 21)), 1u << ((sv[g] >> 16) & 31u));
+          } else {
+            for (int g = 0; g < nt; ++g) {
+              const uint32_t v = smem_u32(SV + (g << 5) + lane);
+              if (v & 0xffffu) atomicOr(smem_u32_ptr(c.bm + (v >> 21)), 1u << ((v >> 16) & 31u));
             }
           }
+          __syncwarp();
+          nnz = bitmap_prefix(c);
+          __syncwarp();
+          const bool save = MODE == MODE_INFER &&
+                            (p.infer_samples == 0 ? it == iters
+                                                  : (it > p.infer_burn_in && (it - p.infer_burn_in) % p.infer_thinning == 0));
+          int32_t* acc = MODE == MODE_INFER ? p.infer_acc + (size_t)d * K : nullptr;  // this warp owns document d
+          if (!WIDE) {
+#pragma unroll
+            for (int g = 0; g < MAXNT; ++g)
+              if (sv[g] & 0xffffu) {
+                p.rows[rp + bitmap_rank(c, (int)(sv[g] >> 16))] = sv[g];
+                if (save) acc[sv[g] >> 16] += (int32_t)(sv[g] & 0xffffu);
+              }
+          } else {
+            for (int g = 0; g < nt; ++g) {
+              const uint32_t v = smem_u32(SV + (g << 5) + lane);
+              if (v & 0xffffu) {
+                p.rows[rp + bitmap_rank(c, (int)(v >> 16))] = v;
+                if (save) acc[v >> 16] += (int32_t)(v & 0xffffu);
+              }
+            }
+          }
+          __syncwarp();  // the row is read back by other lanes at the next iteration's visit start
         }
       }
 
-      if (MODE != MODE_FROZEN) {
-        for (int j = lane; j < nnz; j += 32) p.rows[rp + j] = slots[j];
-        if (lane == 0) p.row_nnz[d] = nnz;
-      }
-      st_nnz += doc_nnz;
+      if (MODE != MODE_FROZEN && lane == 0) p.row_nnz[d] = nnz;
+      // statistics: sum over the document's tokens of its non-zero topics, taken as the mean of the
+      // row width at visit start and end (the kernel does not track the width token by token)
+      st_nnz += (unsigned long long)(te - tb) * (unsigned long long)(nnz_start + nnz) * (unsigned long long)iters / 2ull;
       st_moved += c.st_moved;
       st_prior += c.st_prior;
       c.st_moved = 0;
       c.st_prior = 0;
-      __syncwarp();
     }
   }
 

@@ -80,39 +80,48 @@ void oracle_tile_scan_f32(const float* in, int64_t n, float* out) {
   }
 }
 
-/* Doc-bucket prefix order of the spec ("lane-strided"): slot j of a row of n slots sits on lane
- * j mod 32, tile j div 32, as in the GPU's shared-memory row; NT = floor(n/32)+1 tiles (the row
- * always has room for one more slot). Each lane sums ITS slots tile by tile starting from +0, the
- * 32 lane totals go through the Kogge-Stone scan, and slot j gets  P_j = E_l + (lane-local
- * inclusive sum), E_l = scanned total of lane l-1 (0 for lane 0). The cumulative order is
- * therefore lane-major: (lane 0: slots 0, 32, 64, ...), (lane 1: slots 1, 33, ...), ...
- * *total = the scanned total of lane 31. One warp scan per token whatever the row width. */
-void oracle_lane_strided_prefix_f32(const float* in, int64_t n, float* out, float* total) {
-  const int64_t nt = n / 32 + 1;
+/* Doc-bucket prefix order of the spec ("lane-strided") over a row laid out in nt tiles of 32
+ * slots: slot (g, l) = tile g, lane l, sits at in[32 g + l]. Each lane sums ITS slots tile by tile
+ * starting from +0 (lane-local inclusive sums), the 32 lane totals go through the Kogge-Stone
+ * scan, and slot (g, l) gets  P = E_l + (lane-local inclusive sum), E_l = scanned total of lane
+ * l-1 (0 for lane 0). The cumulative order is therefore lane-major: (lane 0: tiles 0, 1, ...),
+ * (lane 1: ...), ... *total = the scanned total of lane 31. One warp scan per token whatever the
+ * row width. local (may be NULL) receives the lane-local inclusive sums. */
+static void lane_prefix_tiles(const float* in, int32_t nt, float* out, float* local, float* E_out,
+                              float* total) {
   float T[32], y[32];
   for (int l = 0; l < 32; ++l) {
     float run = 0.0f;
-    for (int64_t g = 0; g < nt; ++g) {
-      const int64_t j = 32 * g + l;
-      if (j < n) {
-        run = run + in[j];
-        out[j] = run; /* lane-local for now */
-      }
+    for (int32_t g = 0; g < nt; ++g) {
+      run = run + in[32 * g + l];
+      out[32 * g + l] = run; /* lane-local for now */
     }
     T[l] = run;
   }
+  if (local) memcpy(local, out, sizeof(float) * 32u * (size_t)nt);
   for (int d = 1; d < 32; d <<= 1) {
     for (int l = 0; l < 32; ++l) y[l] = (l >= d) ? (T[l] + T[l - d]) : T[l];
     memcpy(T, y, sizeof(T));
   }
   for (int l = 0; l < 32; ++l) {
     const float E = l == 0 ? 0.0f : T[l - 1];
-    for (int64_t g = 0; g < nt; ++g) {
-      const int64_t j = 32 * g + l;
-      if (j < n) out[j] = E + out[j];
-    }
+    if (E_out) E_out[l] = E;
+    for (int32_t g = 0; g < nt; ++g) out[32 * g + l] = E + out[32 * g + l];
   }
   *total = T[31];
+}
+
+/* Exported building block (tests/test_oracle.py): n slots in positional layout (slot j on lane
+ * j mod 32, tile j div 32), n/32 + 1 tiles, the slots past n weighing +0. */
+void oracle_lane_strided_prefix_f32(const float* in, int64_t n, float* out, float* total) {
+  const int32_t nt = (int32_t)(n / 32 + 1);
+  float* a = (float*)calloc(32u * (size_t)nt, sizeof(float));
+  float* S = (float*)malloc(sizeof(float) * 32u * (size_t)nt);
+  memcpy(a, in, sizeof(float) * (size_t)n);
+  lane_prefix_tiles(a, nt, S, NULL, NULL, total);
+  memcpy(out, S, sizeof(float) * (size_t)n);
+  free(a);
+  free(S);
 }
 
 void oracle_spec_tables(int32_t V, int32_t K, const int32_t* nwk, const int32_t* nk,
@@ -167,58 +176,174 @@ int32_t oracle_spec_hsearch(const float* row, int32_t K, float s) {
   return block;
 }
 
-int32_t oracle_spec_select(int32_t K, const int32_t* slot_topic, const int32_t* slot_count,
-                           int32_t nslots, const int32_t* nwk_row, const float* invden,
-                           const float* ab, const float* prior_row, float q_w, float beta_f,
-                           int32_t old_topic, float u) {
-  /* doc bucket weights, own token excluded from n_wk and n_dk */
-  float stack_a[256] = {0.0f}, stack_s[256];
-  float* a = nslots <= 256 ? stack_a : (float*)malloc(sizeof(float) * (size_t)nslots);
-  float* S = nslots <= 256 ? stack_s : (float*)malloc(sizeof(float) * (size_t)nslots);
-  for (int32_t j = 0; j < nslots; ++j) {
-    int32_t t = slot_topic[j];
-    int32_t c = slot_count[j];
-    int32_t n = nwk_row[t];
-    if (t == old_topic) {
-      c -= 1;
-      n -= 1;
-      if (n < 0) n = 0;
+/* ---- a document's row during one visit (DESIGN.md "sampling spec", v2) ---------------------
+ * The GPU keeps the row in REGISTERS: nt tiles of 32 slots, slot (g, l) on lane l. A slot is
+ * live (count > 0) or dead (count 0: weighs +0). Slots never shift:
+ *   - visit start: the ascending compact list of the document's n non-zero topics is split evenly
+ *     over nt = n/32 + 1 tiles (q = n / nt, r = n % nt: tile g takes q + [g < r] consecutive sorted
+ *     positions starting at g q + min(g, r), on lanes 0, 1, ...); bound[g] = the first topic of
+ *     tile g (g >= 1; K when the tile starts empty);
+ *   - every live slot caches  wt = invden[t] * (float)n_dk  (recomputed, with that product,
+ *     whenever its count changes); the token being resampled weighs  wt - invden[o]  at its slot;
+ *   - a topic leaving the document kills its slot in place; a topic entering it takes the lowest
+ *     dead lane of its preferred tile g* = #{g >= 1 : topic >= bound[g]} or, when that tile is
+ *     full, of the next tile (cyclically) that has a dead slot, the just-vacated slot included;
+ *     when no tile has one, an empty tile is appended (bound = K) and its lane 0 is taken.
+ * Tiles therefore stay (mostly) topic ranges, which is what keeps a tile's 32 n_wk gathers on few
+ * 128-byte lines; nothing else depends on the placement. At the end of the visit the live slots
+ * go back to the document's packed row in ascending topic order. */
+typedef struct {
+  int32_t nt, cap_tiles;
+  int32_t* topic; /* [32 cap_tiles] */
+  int32_t* count;
+  int32_t* bound; /* [cap_tiles] */
+  float *wt, *a, *S, *loc;
+} spec_row;
+
+static void row_alloc(spec_row* r, int64_t max_slots) {
+  r->cap_tiles = (int32_t)(max_slots / 32 + 2);
+  const size_t n = 32u * (size_t)r->cap_tiles;
+  r->topic = (int32_t*)calloc(n, sizeof(int32_t));
+  r->count = (int32_t*)calloc(n, sizeof(int32_t));
+  r->bound = (int32_t*)calloc((size_t)r->cap_tiles, sizeof(int32_t));
+  r->wt = (float*)calloc(n, sizeof(float));
+  r->a = (float*)calloc(n, sizeof(float));
+  r->S = (float*)calloc(n, sizeof(float));
+  r->loc = (float*)calloc(n, sizeof(float));
+  r->nt = 1;
+}
+static void row_free(spec_row* r) {
+  free(r->topic);
+  free(r->count);
+  free(r->bound);
+  free(r->wt);
+  free(r->a);
+  free(r->S);
+  free(r->loc);
+}
+
+/* visit start: ns sorted (topic, count) pairs */
+static void row_init(spec_row* r, int32_t K, const float* invden, const int32_t* st, const int32_t* sc,
+                     int32_t ns) {
+  const int32_t nt = ns / 32 + 1;
+  const int32_t q = ns / nt, rem = ns % nt;
+  r->nt = nt;
+  memset(r->topic, 0, sizeof(int32_t) * 32u * (size_t)nt);
+  memset(r->count, 0, sizeof(int32_t) * 32u * (size_t)nt);
+  memset(r->wt, 0, sizeof(float) * 32u * (size_t)nt);
+  for (int32_t g = 0; g < nt; ++g) {
+    const int32_t b = g * q + (g < rem ? g : rem), e = b + q + (g < rem ? 1 : 0);
+    for (int32_t j = b; j < e; ++j) {
+      r->topic[32 * g + (j - b)] = st[j];
+      r->count[32 * g + (j - b)] = sc[j];
+      r->wt[32 * g + (j - b)] = invden[st[j]] * (float)sc[j];
     }
-    float x = (float)n + beta_f;
-    float y = x * invden[t];
-    a[j] = y * (float)c;
+    r->bound[g] = (g == 0) ? 0 : (b < e ? st[b] : K);
   }
-  float A = 0.0f;
-  oracle_lane_strided_prefix_f32(a, nslots, S, &A);
+}
+
+/* One token: returns the new topic. Doc bucket weights, own token excluded from n_wk and n_dk:
+ *   a = ((float)n_wk' + beta) * wt'   with wt' = wt - invden[o] at the old topic's slot */
+static int32_t row_select(const spec_row* r, int32_t K, const int32_t* nwk_row, const float* invden,
+                          const float* ab, const float* prior_row, float q_w, float beta_f,
+                          int32_t old_topic, float u) {
+  const int32_t nt = r->nt, n = 32 * nt;
+  for (int32_t j = 0; j < n; ++j) {
+    if (r->count[j] == 0) {
+      r->a[j] = 0.0f;
+      continue;
+    }
+    const int32_t t = r->topic[j];
+    int32_t m = nwk_row[t];
+    float wgt = r->wt[j];
+    if (t == old_topic) {
+      m -= 1;
+      wgt = wgt - invden[old_topic];
+    }
+    if (m < 0) m = 0;
+    const float x = (float)m + beta_f;
+    r->a[j] = x * wgt;
+  }
+  float A = 0.0f, E[32];
+  lane_prefix_tiles(r->a, nt, r->S, r->loc, E, &A);
   const float delta = ab[old_topic];
   float qp = q_w - delta;
   if (qp < 0.0f) qp = 0.0f;
   const float T = A + qp;
   const float x = u * T;
-  int32_t result;
   if (x < A) {
-    /* first slot in cumulative (lane-major) order whose prefix exceeds x; none (x within an ulp
-     * of A): the row's last slot */
-    int32_t j = nslots - 1;
-    int found = 0;
-    for (int l = 0; l < 32 && !found; ++l)
-      for (int32_t i = l; i < nslots; i += 32)
-        if (S[i] > x) {
-          j = i;
-          found = 1;
+    /* first slot in cumulative (lane-major) order whose prefix exceeds x. The scanned lane offsets
+     * and the lane-local sums round differently, so within an ulp of a lane boundary that slot can
+     * be one that adds no weight (a dead slot, or the old topic's slot when the token is its only
+     * one), or there is none at all (x within an ulp of A): the token then keeps its topic. */
+    int32_t pick = -1;
+    for (int l = 0; l < 32 && pick < 0; ++l)
+      for (int32_t g = 0; g < nt; ++g)
+        if (r->S[32 * g + l] > x) {
+          pick = 32 * g + l;
           break;
         }
-    result = slot_topic[j];
-  } else {
-    const float y = x - A;
-    const float po = prior_row[old_topic];
-    const float pod = po - delta;
-    const float s = (y < pod) ? y : (y + delta);
-    result = oracle_spec_hsearch(prior_row, K, s);
+    if (pick < 0 || r->count[pick] == 0) return old_topic;
+    if (r->topic[pick] == old_topic && r->count[pick] == 1) return old_topic;
+    return r->topic[pick];
   }
-  if (a != stack_a) free(a);
-  if (S != stack_s) free(S);
-  return result;
+  const float y = x - A;
+  const float po = prior_row[old_topic];
+  const float pod = po - delta;
+  const float s = (y < pod) ? y : (y + delta);
+  return oracle_spec_hsearch(prior_row, K, s);
+}
+
+/* the token moves from topic o to topic n != o */
+static void row_move(spec_row* r, int32_t K, const float* invden, int32_t o, int32_t n) {
+  const int32_t slots = 32 * r->nt;
+  int32_t jo = 0;
+  while (!(r->count[jo] > 0 && r->topic[jo] == o)) ++jo;
+  r->count[jo] -= 1;
+  r->wt[jo] = invden[o] * (float)r->count[jo];
+  for (int32_t j = 0; j < slots; ++j)
+    if (r->count[j] > 0 && r->topic[j] == n) {
+      r->count[j] += 1;
+      r->wt[j] = invden[n] * (float)r->count[j];
+      return;
+    }
+  int32_t gstar = 0;
+  for (int32_t g = 1; g < r->nt; ++g)
+    if (n >= r->bound[g]) ++gstar;
+  for (int32_t i = 0; i < r->nt; ++i) {
+    const int32_t g = (gstar + i) % r->nt;
+    for (int l = 0; l < 32; ++l)
+      if (r->count[32 * g + l] == 0) {
+        r->topic[32 * g + l] = n;
+        r->count[32 * g + l] = 1;
+        r->wt[32 * g + l] = invden[n];
+        return;
+      }
+  }
+  /* every slot is live: append an empty tile, take its lane 0 */
+  if (r->nt >= r->cap_tiles) abort();
+  memset(r->topic + 32 * r->nt, 0, sizeof(int32_t) * 32);
+  memset(r->count + 32 * r->nt, 0, sizeof(int32_t) * 32);
+  memset(r->wt + 32 * r->nt, 0, sizeof(float) * 32);
+  r->bound[r->nt] = K;
+  r->topic[32 * r->nt] = n;
+  r->count[32 * r->nt] = 1;
+  r->wt[32 * r->nt] = invden[n];
+  r->nt += 1;
+}
+
+/* One token against a row given as its visit-start list (slots = the document's sorted non-zero
+ * topics INCLUDING the current token). Returns the new topic. */
+int32_t oracle_spec_select(int32_t K, const int32_t* slot_topic, const int32_t* slot_count,
+                           int32_t nslots, const int32_t* nwk_row, const float* invden,
+                           const float* ab, const float* prior_row, float q_w, float beta_f,
+                           int32_t old_topic, float u) {
+  spec_row r;
+  row_alloc(&r, nslots);
+  row_init(&r, K, invden, slot_topic, slot_count, nslots);
+  const int32_t res = row_select(&r, K, nwk_row, invden, ab, prior_row, q_w, beta_f, old_topic, u);
+  row_free(&r);
+  return res;
 }
 
 /* ---- drivers ---------------------------------------------------------------------------- */
@@ -261,6 +386,8 @@ void oracle_spec_frozen(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
   int32_t* dense = (int32_t*)calloc((size_t)K, sizeof(int32_t));
   int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
   int32_t* sc = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+  spec_row r;
+  row_alloc(&r, K);
   for (int64_t d = 0; d < D; ++d) {
     for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z_in[i]]++;
     int32_t ns = 0;
@@ -271,13 +398,15 @@ void oracle_spec_frozen(int64_t D, int32_t V, int32_t K, const int64_t* doc_ptr,
         dense[k] = 0;
         ++ns;
       }
+    row_init(&r, K, t.invden, st, sc, ns);
     for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
       int32_t w = tok_word[i];
       float u = uniforms ? uniforms[i] : token_uniform(seed, global_off + i, sweep);
-      z_out[i] = oracle_spec_select(K, st, sc, ns, nwk + (size_t)w * K, t.invden, t.ab,
-                                    t.prior + (size_t)w * K, t.q[w], beta_f, z_in[i], u);
+      z_out[i] = row_select(&r, K, nwk + (size_t)w * K, t.invden, t.ab, t.prior + (size_t)w * K, t.q[w],
+                            beta_f, z_in[i], u);
     }
   }
+  row_free(&r);
   free(dense);
   free(st);
   free(sc);
@@ -316,6 +445,8 @@ void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64
   }
   if (delta_nwk) memset(delta_nwk, 0, sizeof(int32_t) * (size_t)V * (size_t)K);
   if (delta_nk) memset(delta_nk, 0, sizeof(int32_t) * (size_t)K);
+  spec_row r;
+  row_alloc(&r, K);
   for (int64_t d = 0; d < D; ++d) {
     for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) dense[z[i]]++;
     int32_t ns = 0;
@@ -326,6 +457,7 @@ void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64
         dense[k] = 0;
         ++ns;
       }
+    row_init(&r, K, t.invden, st, sc, ns);
     for (int64_t i = doc_ptr[d]; i < doc_ptr[d + 1]; ++i) {
       const int32_t w = tok_word[i];
       const int32_t o = z[i];
@@ -336,28 +468,9 @@ void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64
         shifted[o] += 1;
         row = shifted;
       }
-      const int32_t n = oracle_spec_select(K, st, sc, ns, row, t.invden, t.ab, t.prior + (size_t)w * K,
-                                           t.q[w], beta_f, o, u);
+      const int32_t n = row_select(&r, K, row, t.invden, t.ab, t.prior + (size_t)w * K, t.q[w], beta_f, o, u);
       if (n != o) {
-        /* remove one from o (delete slot if it empties), add one to n (sorted insert) */
-        int32_t jo = 0;
-        while (st[jo] != o) ++jo;
-        if (--sc[jo] == 0) {
-          memmove(st + jo, st + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
-          memmove(sc + jo, sc + jo + 1, sizeof(int32_t) * (size_t)(ns - jo - 1));
-          --ns;
-        }
-        int32_t jn = 0;
-        while (jn < ns && st[jn] < n) ++jn;
-        if (jn < ns && st[jn] == n) {
-          sc[jn]++;
-        } else {
-          memmove(st + jn + 1, st + jn, sizeof(int32_t) * (size_t)(ns - jn));
-          memmove(sc + jn + 1, sc + jn, sizeof(int32_t) * (size_t)(ns - jn));
-          st[jn] = n;
-          sc[jn] = 1;
-          ++ns;
-        }
+        row_move(&r, K, t.invden, o, n);
         z[i] = n;
         if (live) {
           nwk[(size_t)w * K + o]--;
@@ -374,6 +487,7 @@ void oracle_spec_sweep_given_counts(int64_t D, int32_t V, int32_t K, const int64
       }
     }
   }
+  row_free(&r);
   free(shifted);
   free(dense);
   free(st);

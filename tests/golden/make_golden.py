@@ -64,7 +64,8 @@ def tiny():
 def frozen():
     out = {}
     for name, (D, V, mean_len, kt, K) in {"k4": (40, 30, 12.0, 4, 4), "k20": (60, 80, 30.0, 8, 20),
-                                          "k100": (40, 120, 90.0, 20, 100), "k1500": (12, 60, 220.0, 10, 1500)}.items():
+                                          "k100": (40, 120, 90.0, 20, 100), "k1500": (12, 60, 220.0, 10, 1500),
+                                          "k3000": (6, 60, 600.0, 10, 3000)}.items():  # k3000: rows wider than 8 tiles
         dp, tok = O.gen_corpus(D, V, mean_len, kt, 77)
         z = O.init_z(len(tok), K, 31)
         z = O.spec_sweeps(dp, tok, z, V, K, 0.1, 0.01, 31, 1, 2)  # a non-uniform snapshot

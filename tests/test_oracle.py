@@ -171,7 +171,7 @@ def test_spec_sampler_on_wide_rows_draws_from_the_spec_conditional(oracle, K, do
 
 def test_frozen_triples_regression(oracle):
     g = np.load(os.path.join(GOLD, "frozen_triples.npz"))
-    for name in ("k4", "k20", "k100", "k1500"):
+    for name in ("k4", "k20", "k100", "k1500", "k3000"):
         D, V, K = [int(x) for x in g[name + "_meta"]]
         dp, tok, z, u = g[name + "_doc_ptr"], g[name + "_tok"], g[name + "_z"], g[name + "_u"]
         assert np.array_equal(oracle.spec_frozen(dp, tok, z, V, K, ALPHA, BETA, 31, 1, uniforms=u), g[name + "_expected_u"])
