@@ -72,7 +72,8 @@ typedef struct {
   int32_t device;               /* CUDA ordinal                                               */
   int32_t rank;                 /* AD-LDA shard id, 0..world_size-1                           */
   int32_t world_size;           /* number of shards (setNumThreads(n) analogue), >= 1         */
-  int32_t reserved0;
+  int32_t table_refresh;        /* LIVE mode: rebuilds of the per-sweep tables per sweep (1..32);
+                                   0 = auto: as many as cost <= ~5 % of a sweep, 16 at most    */
   int64_t global_token_offset;  /* global index of this shard's first token (Philox counter)  */
   int64_t global_doc_offset;    /* global index of this shard's first document                */
   void* stream;                 /* cudaStream_t to enqueue on, or NULL to create a private one */

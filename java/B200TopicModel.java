@@ -48,7 +48,7 @@ public class B200TopicModel implements Serializable, AutoCloseable {
       JAVA_INT.withName("struct_size"), JAVA_INT.withName("num_topics"), JAVA_INT.withName("num_types"),
       JAVA_INT.withName("mode"), JAVA_DOUBLE.withName("alpha_sum"), JAVA_DOUBLE.withName("beta"),
       JAVA_LONG.withName("seed"), JAVA_INT.withName("device"), JAVA_INT.withName("rank"),
-      JAVA_INT.withName("world_size"), JAVA_INT.withName("reserved0"), JAVA_LONG.withName("global_token_offset"),
+      JAVA_INT.withName("world_size"), JAVA_INT.withName("table_refresh"), JAVA_LONG.withName("global_token_offset"),
       JAVA_LONG.withName("global_doc_offset"), ADDRESS.withName("stream"));
 
   private static final MethodHandle LAST_ERROR = fn("b200lda_last_error", FunctionDescriptor.of(ADDRESS));

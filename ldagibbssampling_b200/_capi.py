@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200lda.so")
+# B200LDA_LIB: load another build of the same library (kernel-tuning experiments, tools/)
+LIB_PATH = os.environ.get("B200LDA_LIB") or os.path.join(_HERE, "libb200lda.so")
 
 MODE_LIVE = 0
 MODE_DEFERRED = 1
@@ -33,7 +34,7 @@ class Config(C.Structure):
         ("struct_size", C.c_int32), ("num_topics", C.c_int32), ("num_types", C.c_int32),
         ("mode", C.c_int32), ("alpha_sum", C.c_double), ("beta", C.c_double), ("seed", C.c_uint64),
         ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
-        ("reserved0", C.c_int32), ("global_token_offset", C.c_int64),
+        ("table_refresh", C.c_int32), ("global_token_offset", C.c_int64),
         ("global_doc_offset", C.c_int64), ("stream", C.c_void_p),
     ]
 
@@ -135,12 +136,12 @@ class Sampler:
     """One context = one GPU = one AD-LDA shard. Thin, 1:1 over the C ABI; host numpy in/out."""
 
     def __init__(self, num_topics, num_types, alpha_sum, beta, seed=0, mode=MODE_LIVE, device=0,
-                 rank=0, world_size=1, global_token_offset=0, global_doc_offset=0, stream=None):
+                 rank=0, world_size=1, global_token_offset=0, global_doc_offset=0, stream=None, table_refresh=0):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = Config(struct_size=C.sizeof(Config), num_topics=num_topics, num_types=num_types,
                      mode=mode, alpha_sum=alpha_sum, beta=beta, seed=seed, device=device, rank=rank,
-                     world_size=world_size, reserved0=0, global_token_offset=global_token_offset,
+                     world_size=world_size, table_refresh=table_refresh, global_token_offset=global_token_offset,
                      global_doc_offset=global_doc_offset, stream=stream)
         self.K, self.V = num_topics, num_types
         self.device = device

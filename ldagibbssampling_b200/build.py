@@ -45,19 +45,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = None) -> str:
+    """out: write the library somewhere else (tuning variants, see tools/build_variants.sh)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
     extra = os.environ.get("B200LDA_NVCC_EXTRA", "").split()
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "b200lda.cu")]
+          ["-I", INCLUDE, "-o", out or LIB_PATH, os.path.join(CSRC, "b200lda.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libb200lda.so")
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out))

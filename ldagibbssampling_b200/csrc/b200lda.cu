@@ -60,6 +60,7 @@ constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
 constexpr int kCounters = 12;  // [9..11] sink for the stats of inference passes
 constexpr int kMaxClasses = 16;
+constexpr int kMaxSegments = 32;  // table rebuilds per LIVE sweep (b200lda_ctx::table_refresh)
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 constexpr int kPartial = 1184;   // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
 
@@ -136,10 +137,13 @@ struct b200lda_ctx {
   DeviceCorpus corp;  // training documents
   std::vector<SweepShape> shape_cache;  // launch shapes by (row class, tiles): computed once per context
   int class_streams = 0;  // see launch_sweep
+  int max_ctas = 0;       // B200LDA_MAX_CTAS (experiments): cap on the sampling kernel's grid, 0 = none
+  int table_refresh = 0;  // LIVE mode: table rebuilds per sweep; 0 = auto (auto_table_refresh)
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
   float *d_invden = nullptr, *d_ab = nullptr, *d_prior = nullptr, *d_q = nullptr, *d_alpha_f = nullptr;
+  float *d_prior_bg = nullptr, *d_q_bg = nullptr, *d_invden_bg = nullptr;  // sweep-start tables for the background classes
   double *d_alpha = nullptr, *d_lg_alpha = nullptr;
   std::vector<double> alpha;
   double alpha_sum = 0.0, beta = 0.0;
@@ -558,10 +562,11 @@ int build_doc_rows(b200lda_ctx* c, DeviceCorpus& cp) {
 
 // ---- per-sweep pieces ---------------------------------------------------------------------------
 
-int build_tables(b200lda_ctx* c) {
+int build_tables(b200lda_ctx* c, bool with_delta = false) {
   const float beta_f = (float)c->beta;
   const float vbeta = (float)c->V * beta_f;
-  k_topic_tables<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_alpha_f, vbeta, c->d_invden, c->d_ab);
+  k_topic_tables<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, with_delta ? c->d_nk_delta : nullptr,
+                                                           c->d_alpha_f, vbeta, c->d_invden, c->d_ab);
   k_prior_rows<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_nwk, c->d_ab, beta_f,
                                                                             c->layout, c->d_prior, c->d_q);
   c->launches += 2;
@@ -599,16 +604,37 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
   return p;
 }
 
+// LIVE mode reads the prior bucket (49 % of the draws at K = 1000, alpha_k = 0.1) from tables built
+// from n_wk / n_k as they stood at the last rebuild. Rebuilt once per sweep the chain mixes like
+// Mallet with twice as many threads (LL/token 4 % behind the single chain at sweep 25 on the
+// C4-shaped 20 k-document sample, profiles/r02_ll_parity.md); 16 rebuilds bring it within 1.5 %.
+// A rebuild streams n_wk and the prefix table once (8 V K bytes) and splits every bulk class
+// into one more launch. Auto: as many rebuilds as cost at most ~5 % of the sweep (a few ms on
+// corpora whose sweeps are that short: nobody waits for them), 16 at most.
+int auto_table_refresh(const b200lda_ctx* c, const DeviceCorpus& cp) {
+  const double sweep_ms = (double)cp.N / 3.0e6;
+  const double rebuild_ms = 8.0 * (double)c->V * (double)c->K / 5.0e9 + 0.1 * (double)std::max<size_t>(1, cp.classes.size());
+  const double budget_ms = std::max(0.05 * sweep_ms, 5.0 - 0.2 * sweep_ms);
+  return (int)std::max(1.0, std::min(16.0, std::floor(budget_ms / rebuild_ms)));
+}
+
+// seg / nseg: the launch covers the seg-th of nseg equal ranges of the class's scheduler chunks
+// (chunks are strided through the longest-first order, so every range is a cross-section).
 template <int MODE, bool LIVE>
 int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
-                 unsigned long long* counter, cudaStream_t stream, int max_ctas = 0) {
+                 unsigned long long* counter, cudaStream_t stream, int max_ctas = 0, int seg = 0, int nseg = 1) {
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
   p.cap_tiles = sh.cap_tiles;
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
-  const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  const int64_t nchunks = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  p.chunk_begin = (unsigned long long)(nchunks * seg / nseg);
+  p.chunk_end = (unsigned long long)(nchunks * (seg + 1) / nseg);
+  if (p.chunk_end <= p.chunk_begin) return B200LDA_OK;
+  const int64_t warps_needed = (int64_t)(p.chunk_end - p.chunk_begin);
+  if (c->max_ctas > 0) max_ctas = max_ctas > 0 ? std::min(max_ctas, c->max_ctas) : c->max_ctas;
   const int grid_cap = max_ctas > 0 ? std::min(max_ctas, sh.ctas) : sh.ctas;
   const int ctas = (int)std::max<int64_t>(
       1, std::min<int64_t>(grid_cap, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
@@ -676,28 +702,60 @@ void retune_background(b200lda_ctx* c, DeviceCorpus& cp) {
 // context's stream with a reduced grid, and the sweep joins them: a long document's latency is
 // hidden behind the bulk, and its CTAs do not take bulk CTAs' register-file slots on every SM.
 template <int MODE, bool LIVE>
-int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p) {
+int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p_in, int segments = 1) {
   retune_background(c, cp);
+  SweepParams p = p_in;
   if (MODE != MODE_INFER) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
-  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
-  if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
+  segments = std::max(1, std::min(segments, kMaxSegments));
+  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses * kMaxSegments, c->stream));
   // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = the policy above (default);
   // 1 = everything in sequence; 2 = every class forked at full size.
   std::vector<bool> forked(n, false);
+  bool any_fork = false;
   for (size_t i = 0; i + 1 < n; ++i) {
-    const DeviceCorpus::DocClass& dc = cp.classes[i];
-    const bool fork = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
-    forked[i] = fork;
-    cudaStream_t st = fork ? c->side[i] : c->stream;
-    if (fork) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-    TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i, st,
-                                  c->class_streams == 0 ? dc.side_ctas : 0)));
-    if (fork) CU(cudaEventRecord(c->ev_join[i], st));
+    forked[i] = c->class_streams == 2 || (c->class_streams == 0 && cp.classes[i].side_ctas > 0);
+    any_fork = any_fork || forked[i];
   }
-  TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
-                                c->d_sched + (n - 1), c->stream)));
+  SweepParams pbg = p;  // tables the background classes read for the whole sweep
+  if (segments > 1 && any_fork) {
+    // The bulk's tables are rebuilt between segments while the background classes are still
+    // running: those keep a copy of the sweep-start tables.
+    const size_t pw = (size_t)c->V * c->layout.stride;
+    if (!c->d_prior_bg) {
+      TRY(dev_alloc_t(c, &c->d_prior_bg, pw));
+      TRY(dev_alloc_t(c, &c->d_q_bg, (size_t)c->V));
+      TRY(dev_alloc_t(c, &c->d_invden_bg, (size_t)2 * c->K));
+    }
+    CU(cudaMemcpyAsync(c->d_prior_bg, c->d_prior, sizeof(float) * pw, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_q_bg, c->d_q, sizeof(float) * c->V, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_invden_bg, c->d_invden, sizeof(float) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_invden_bg + c->K, c->d_ab, sizeof(float) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+    pbg.prior = c->d_prior_bg;
+    pbg.q = c->d_q_bg;
+    pbg.invden = c->d_invden_bg;
+    pbg.ab = c->d_invden_bg + c->K;
+  }
+  if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
+  for (size_t i = 0; i + 1 < n; ++i) {
+    if (!forked[i]) continue;
+    const DeviceCorpus::DocClass& dc = cp.classes[i];
+    cudaStream_t st = c->side[i];
+    CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+    TRY((launch_class<MODE, LIVE>(c, pbg, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments, st,
+                                  c->class_streams == 0 ? dc.side_ctas : 0)));
+    CU(cudaEventRecord(c->ev_join[i], st));
+  }
+  for (int seg = 0; seg < segments; ++seg) {
+    if (seg > 0) TRY(build_tables(c, true));  // LIVE: prior rows and 1/(n_k + V beta) from the counts as they stand
+    for (size_t i = 0; i < n; ++i) {
+      if (i + 1 < n && forked[i]) continue;
+      const DeviceCorpus::DocClass& dc = cp.classes[i];
+      TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments + seg, c->stream, 0,
+                                    seg, segments)));
+    }
+  }
   if (n > 1) {
     CU(cudaEventRecord(c->ev_bulk, c->stream));
     c->timed_corpus = &cp;
@@ -806,6 +864,9 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->layout = make_layout(c->K);
   if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
+  if (const char* e = std::getenv("B200LDA_MAX_CTAS")) c->max_ctas = atoi(e);
+  c->table_refresh = std::max(0, std::min((int)cfg->table_refresh, kMaxSegments));
+  if (const char* e = std::getenv("B200LDA_TABLE_REFRESH")) c->table_refresh = std::max(0, std::min(atoi(e), kMaxSegments));
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {
@@ -836,7 +897,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses * kMaxSegments)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
@@ -867,6 +928,9 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_ab);
   dev_free(c->d_prior);
   dev_free(c->d_q);
+  dev_free(c->d_prior_bg);
+  dev_free(c->d_q_bg);
+  dev_free(c->d_invden_bg);
   dev_free(c->d_alpha_f);
   dev_free(c->d_alpha);
   dev_free(c->d_lg_alpha);
@@ -981,7 +1045,7 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   if (deferred)
     TRY((launch_sweep<MODE_UPDATE, false>(c, c->corp, p)));
   else
-    TRY((launch_sweep<MODE_UPDATE, true>(c, c->corp, p)));
+    TRY((launch_sweep<MODE_UPDATE, true>(c, c->corp, p, c->table_refresh > 0 ? c->table_refresh : auto_table_refresh(c, c->corp))));
   CU(cudaEventRecord(c->ev[2], c->stream));
   if (multi) {
     const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;

@@ -66,6 +66,7 @@ struct SweepParams {
   uint32_t sweep;
   int64_t global_tok_off;
   unsigned long long* doc_counter;  // dynamic document scheduler: next chunk index (starts at 0 for each launch)
+  unsigned long long chunk_begin, chunk_end;  // this launch's range of scheduler chunks (a segment of the class)
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
   unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
   // MODE_INFER: iterations 1..infer_iters per document (Philox sweep key = iteration); a sample is
@@ -96,10 +97,10 @@ __host__ __device__ constexpr int rowclass_max_len(int rc) { return 32 * rowclas
 #define B200LDA_TOP_EARLY_NT 3  // rows of up to this many tiles request the prior's top level at the start of the token step
 #endif
 #ifndef B200LDA_RC0_MIN_CTAS
-#define B200LDA_RC0_MIN_CTAS 5
+#define B200LDA_RC0_MIN_CTAS 6  // 40 registers, no spills: 48 warps per SM (measured: C4 29.9 -> 28.5 ms)
 #endif
 #ifndef B200LDA_RC1_MIN_CTAS
-#define B200LDA_RC1_MIN_CTAS 4
+#define B200LDA_RC1_MIN_CTAS 5
 #endif
 #ifndef B200LDA_RC2_MIN_CTAS
 #define B200LDA_RC2_MIN_CTAS 4
@@ -200,13 +201,16 @@ struct WarpCtx {
 // per 32-token batch (one lane per token) and, for narrow rows, this lane's entry of the top search
 // level is requested at the start of the token step, before the bucket is known. A draw that lands
 // in the prior bucket then pays one dependent memory access per remaining level only.
-__device__ __forceinline__ float prior_top_entry(const SweepParams& p, const WarpCtx& c, int w) {
-  const float* prow = p.prior + (size_t)w * p.layout.stride;
-  return (c.top_lane >= 0) ? __ldg(prow + c.top_lane) : 0.0f;
+__device__ __forceinline__ const float* prior_row_ptr(const SweepParams& p, uint32_t w) {
+  const char* r = reinterpret_cast<const char*>(p.prior) + (size_t)w * (size_t)(4u * (uint32_t)p.layout.stride);
+  asm volatile("" : "+l"(r));  // opaque: one IMAD.WIDE per token, every level load is an offset from it
+  return reinterpret_cast<const float*>(r);
 }
-__device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int K, int w, float po, float y, float delta,
-                                            float vtop) {
-  const float* prow = p.prior + (size_t)w * p.layout.stride;
+__device__ __forceinline__ float prior_top_entry(const float* prow, const WarpCtx& c) {
+  return (c.top_lane >= 0) ? __ldg(prow + (uint32_t)c.top_lane) : 0.0f;
+}
+__device__ __forceinline__ int prior_search(const SweepParams& p, const float* prow, int lane, int K, float po, float y,
+                                            float delta, float vtop) {
   const float pod = fsub(po, delta);
   const float s = (y < pod) ? y : fadd(y, delta);
   const int top = p.layout.nlev - 1;
@@ -217,7 +221,7 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int 
     const int lo = block << 5;
     const int nvalid = min(32, p.layout.size[lev] - lo);
     float v = 0.0f;
-    if (lane < nvalid) v = __ldg(prow + p.layout.off[lev] + lo + lane);
+    if (lane < nvalid) v = __ldg(prow + (uint32_t)(p.layout.off[lev] + lo + lane));
     const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
     block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
   }
@@ -225,7 +229,7 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, int lane, int 
     const int lo = block << 5;
     const int nvalid = min(32, K - lo);
     float v = 0.0f;
-    if (lane < nvalid) v = __ldg(prow + lo + lane);
+    if (lane < nvalid) v = __ldg(prow + (uint32_t)(lo + lane));
     const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
     block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
   }
@@ -313,19 +317,22 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
   const int lane = c.lane;
   const uint4 ta = lds_u128(tok_addr);       // word, old topic, uniform, Q_w
   const uint4 tb = lds_u128(tok_addr + 16);  // invden[o], ab[o] (0 in inference), P_w[o], next token's word
-  const int w = (int)ta.x, o = (int)ta.y;
+  const uint32_t w = ta.x;
+  const int o = (int)ta.y;
   const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
   const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
   const char* nwk_bytes = reinterpret_cast<const char*>(p.nwk_read);
-  const char* nrow_next = nwk_bytes + (size_t)tb.w * (size_t)c.row_bytes;
-  asm volatile("" : "+l"(nrow_next));  // opaque: per-gather address = one IMAD.WIDE off this pointer
+  const char* nrow_next_b = nwk_bytes + (size_t)tb.w * (size_t)c.row_bytes;
+  asm volatile("" : "+l"(nrow_next_b));  // opaque: per-gather address = one IMAD.WIDE off this pointer
+  const int32_t* nrow_next = reinterpret_cast<const int32_t*>(nrow_next_b);
   int nvn[NT];
 #pragma unroll
   for (int g = 0; g < NT; ++g)  // a dead slot reads a valid cell; its weight is +0
-    nvn[g] = count_load<LIVE>(reinterpret_cast<const int32_t*>(nrow_next + ((size_t)(sv[g] >> 16) << 2)));
+    nvn[g] = count_load<LIVE>(nrow_next + (sv[g] >> 16));
+  const float* prow = prior_row_ptr(p, w);
   constexpr bool kTopEarly = NT <= TE;  // request the prior's top level before the bucket is known
   float vtop = 0.0f;
-  if (kTopEarly) vtop = prior_top_entry(p, c, w);
+  if (kTopEarly) vtop = prior_top_entry(prow, c);
   // a live slot of topic o reads (o << 16) + count with 1 <= count <= 0xffff
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
   // Lane-strided prefix: the lane sums its own slots tile by tile (from +0), ONE warp scan runs over
@@ -367,15 +374,15 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
     if (b != 0u && (pk & 0xffffu) != 0u && pk != okey) newt = (int)(pk >> 16);
   } else {
     ++c.st_prior;
-    if (!kTopEarly) vtop = prior_top_entry(p, c, w);
-    newt = prior_search(p, lane, c.K, w, __uint_as_float(tb.z), fsub(x, A), delta, vtop);
+    if (!kTopEarly) vtop = prior_top_entry(prow, c);
+    newt = prior_search(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, vtop);
   }
 
   if (MODE != MODE_FROZEN && __any_sync(kFullMask, newt != o)) {
     ++c.st_moved;
     const float inv_n = TS ? lds_f32(c.sbase + ((uint32_t)newt << 2)) : __ldg(p.invden + newt);
     const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
-    const bool same_word = LIVE && (int)tb.w == w;
+    const bool same_word = LIVE && tb.w == w;
     // Each lane edits its own slots: -1 at the old topic's slot (it dies in place at count 0),
     // +1 at the new topic's slot when the document already has it.
     bool has_new = false;
@@ -415,14 +422,14 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
         gsel = gany;
         msel = many;
       }
-      if (NT < MAXNT && gsel < 0) {  // every slot live: append a tile (its registers are already dead slots)
+      if (gsel < 0) {  // every slot live: append a tile (its registers are already dead slots)
         gsel = NT;
-        msel = 1u;
+        msel = NT < MAXNT ? 1u : 0u;  // NT == MAXNT: nt = MAXNT + 1 tells the caller to continue in shared memory
         nt = NT + 1;
       }
       if (lane == __ffs(msel) - 1) {
         // the next token's count at the slot's new topic, requested before this token's +1 is issued
-        const int fresh = count_load<LIVE>(reinterpret_cast<const int32_t*>(nrow_next + ((size_t)newt << 2))) + (same_word ? 1 : 0);
+        const int fresh = count_load<LIVE>(nrow_next + (uint32_t)newt) + (same_word ? 1 : 0);
 #pragma unroll
         for (int g = 0; g < (NT < MAXNT ? NT + 1 : NT); ++g) {
           if (g == gsel) {
@@ -436,12 +443,12 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
     // count moves: -1 at the old topic from lane 0, +1 at the new topic from lane 1
     if (LIVE || p.nwk_write != nullptr) {
       if (lane < 2) {
-        const int topic = lane == 0 ? o : newt;
+        const uint32_t topic = (uint32_t)(lane == 0 ? o : newt);
         const int val = lane == 0 ? -1 : 1;
         char* wbase = LIVE ? const_cast<char*>(nwk_bytes) : reinterpret_cast<char*>(p.nwk_write);
-        atomicAdd(reinterpret_cast<int32_t*>(wbase + (size_t)w * (size_t)c.row_bytes + ((size_t)topic << 2)), val);
+        atomicAdd(reinterpret_cast<int32_t*>(wbase + (size_t)w * (size_t)c.row_bytes) + topic, val);
         if (TS) {
-          reds_add_i32(c.sbase + 2u * c.row_bytes + ((uint32_t)topic << 2), val);
+          reds_add_i32(c.sbase + 2u * c.row_bytes + (topic << 2), val);
         } else {
           atomicAdd(p.nk_delta + topic, val);
         }
@@ -453,6 +460,43 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
   return newt;
 }
 
+// Wide path: a topic new to the document takes the lowest dead lane of its preferred tile, else of
+// the next tile (cyclically) that has a dead slot, else lane 0 of an appended tile.
+__device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt, float inv_n) {
+  const int lane = c.lane;
+  const int SV = c.row, WT = c.row + 32 * c.capT, BD = c.row + 96 * c.capT;
+  const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
+  int ge = 0;
+  for (int g = 1 + lane; g < nt; g += 32) ge += (newt >= (int)smem_u32(BD + g)) ? 1 : 0;
+  const int gstar = __reduce_add_sync(kFullMask, ge);
+  int gsel = -1;
+  unsigned msel = 0u;
+  for (int i = 0; i < nt; ++i) {
+    int g = gstar + i;
+    if (g >= nt) g -= nt;
+    const unsigned dm = __ballot_sync(kFullMask, (smem_u32(SV + (g << 5) + lane) & 0xffffu) == 0u);
+    if (dm) {
+      gsel = g;
+      msel = dm;
+      break;
+    }
+  }
+  if (gsel < 0) {  // every slot live: append an empty tile (nt < capT by the class's document lengths)
+    gsel = nt;
+    msel = 1u;
+    smem_u32(SV + (nt << 5) + lane) = 0u;
+    smem_f32(WT + (nt << 5) + lane) = 0.0f;
+    if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
+    nt += 1;
+    __syncwarp();
+  }
+  if (lane == __ffs(msel) - 1) {
+    smem_u32(SV + (gsel << 5) + lane) = nkey;
+    smem_f32(WT + (gsel << 5) + lane) = inv_n;
+  }
+  __syncwarp();
+}
+
 // ---- wide path: row in shared memory, loops over tiles ---------------------------------------------
 template <int MODE, bool LIVE, bool TS>
 __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c, int& nt, int tok) {
@@ -460,9 +504,11 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
   const int lane = c.lane;
   const int SV = c.row, WT = c.row + 32 * c.capT, PS = c.row + 64 * c.capT, BD = c.row + 96 * c.capT;
   const uint4 ta = smem_u128(tok);
-  const int w = (int)ta.x, o = (int)ta.y;
+  const uint32_t w = ta.x;
+  const int o = (int)ta.y;
   const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
-  const int32_t* nrow = p.nwk_read + (size_t)w * c.K;
+  const int32_t* nrow = p.nwk_read + (size_t)w * (size_t)(uint32_t)c.K;
+  const float* prow = prior_row_ptr(p, w);
   const uint4 tb = smem_u128(tok + 4);
   const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
@@ -521,7 +567,7 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
     }
   } else {
     ++c.st_prior;
-    newt = prior_search(p, lane, c.K, w, __uint_as_float(tb.z), fsub(x, A), delta, prior_top_entry(p, c, w));
+    newt = prior_search(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, prior_top_entry(prow, c));
   }
 
   if (MODE != MODE_FROZEN && newt != o) {
@@ -543,49 +589,23 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
       has_new = has_new || in;
     }
     __syncwarp();
-    if (!doc_bucket && !__any_sync(kFullMask, has_new)) {
-      int ge = 0;
-      for (int g = 1 + lane; g < nt; g += 32) ge += (newt >= (int)smem_u32(BD + g)) ? 1 : 0;
-      const int gstar = __reduce_add_sync(kFullMask, ge);
-      int gsel = -1;
-      unsigned msel = 0u;
-      for (int i = 0; i < nt; ++i) {
-        int g = gstar + i;
-        if (g >= nt) g -= nt;
-        const unsigned dm = __ballot_sync(kFullMask, (smem_u32(SV + (g << 5) + lane) & 0xffffu) == 0u);
-        if (dm) {
-          gsel = g;
-          msel = dm;
-          break;
-        }
-      }
-      if (gsel < 0) {  // every slot live: append an empty tile (nt < capT by the class's document lengths)
-        gsel = nt;
-        msel = 1u;
-        smem_u32(SV + (nt << 5) + lane) = 0u;
-        smem_f32(WT + (nt << 5) + lane) = 0.0f;
-        if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
-        nt += 1;
-        __syncwarp();
-      }
-      if (lane == __ffs(msel) - 1) {
-        smem_u32(SV + (gsel << 5) + lane) = nkey;
-        smem_f32(WT + (gsel << 5) + lane) = inv_n;
-      }
-      __syncwarp();
-    }
-    count_moves(p, c, write_row<LIVE>(p, nrow, w, c.K), o, newt);
+    if (!doc_bucket && !__any_sync(kFullMask, has_new)) wide_insert(c, nt, newt, inv_n);
+    count_moves(p, c, write_row<LIVE>(p, nrow, (int)w, c.K), o, newt);
   }
   return newt;
 }
 
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM, int ROWCLASS>
 __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_sweep(const SweepParams p) {
-  constexpr bool WIDE = ROWCLASS == kWideClass;
-  constexpr int MAXNT = WIDE ? 1 : rowclass_max_tiles(ROWCLASS);
+  // The wide class is a hybrid: a visit keeps the row in registers while it fits 8 tiles and moves it
+  // to shared memory when it starts wider or grows a 9th tile (long documents on few topics, and
+  // C3's 333-token documents with ~160 topics, stay on the register path).
+  constexpr bool HYBRID = ROWCLASS == kWideClass;
+  constexpr int MAXNT = HYBRID ? 8 : rowclass_max_tiles(ROWCLASS);
   // Rows up to kTE tiles request the prior's top search level at the start of the token step.
   constexpr int kTE = ROWCLASS <= 1 ? 5 : B200LDA_TOP_EARLY_NT;
-  const int lane = threadIdx.x & 31;
+  int lane = threadIdx.x & 31;
+  asm volatile("" : "+r"(lane));  // opaque: otherwise rematerialised (S2R + LOP) at every use in the token step
   const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
   const int K = p.K;
 
@@ -616,6 +636,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   c.batch_addr = c.sbase + 4u * (uint32_t)c.batch;
   asm volatile("" : "+r"(c.batch_addr));
   c.row_bytes = 4u * (uint32_t)K;
+  asm volatile("" : "+r"(c.row_bytes));
   const int SV = c.row, WT = c.row + 32 * c.capT, BD = c.row + 96 * c.capT;
 
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
@@ -629,9 +650,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   const unsigned long long nchunks = (ndocs + (unsigned long long)p.doc_chunk - 1) / (unsigned long long)p.doc_chunk;
   for (;;) {
     unsigned long long ci = 0;
-    if (lane == 0) ci = atomicAdd(p.doc_counter, 1ull);
+    if (lane == 0) ci = p.chunk_begin + atomicAdd(p.doc_counter, 1ull);
     ci = __shfl_sync(kFullMask, ci, 0);
-    if (ci >= nchunks) break;
+    if (ci >= p.chunk_end) break;
 
     for (unsigned long long di = ci; di < ndocs; di += nchunks) {
       // the document's header, read by lane 0 and broadcast: warp-uniform for the compiler too
@@ -660,8 +681,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
         uint32_t sv[MAXNT];
         float wt[MAXNT];
         int nv[MAXNT];
-        int bnd = 0x7fffffff;  // register classes: first topic of tile `lane` (1 <= lane < nt)
-        if (!WIDE) {
+        int bnd = 0x7fffffff;  // register path: first topic of tile `lane` (1 <= lane < nt)
+        bool wide = HYBRID && nt > MAXNT;
+        if (!wide) {
 #pragma unroll
           for (int g = 0; g < MAXNT; ++g) {
             sv[g] = 0u;
@@ -722,7 +744,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
               make_uint4(__float_as_uint(inv_l), __float_as_uint(dl_l), __float_as_uint(po_l), (uint32_t)wn_l);
           __syncwarp();
           int new_l = o_l;
-          if (!WIDE) {  // the batch's first token: nobody requested its counts
+          if (!wide) {  // the batch's first token: nobody requested its counts
             const int w0 = __shfl_sync(kFullMask, w_l, 0);
             const int32_t* nrow0 = p.nwk_read + (size_t)w0 * K;
 #pragma unroll
@@ -733,7 +755,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
           uint32_t tok_addr = c.batch_addr;
           for (int t = 0; t < cnt; ++t, tok_addr += 32u) {
             int newt;
-            if (WIDE) {
+            if (wide) {
               newt = token_step_wide<MODE, LIVE, TABLES_IN_SMEM>(p, c, nt, c.batch + 8 * t);
             } else {
               // nt is uniform across the warp; instantiations beyond the class's widest row are not generated
@@ -747,6 +769,20 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
               else if (nt == 7) newt = B200LDA_STEP(7);
               else newt = B200LDA_STEP(8);
 #undef B200LDA_STEP
+              if (HYBRID && nt > MAXNT) {
+                // the row needs a 9th tile: it moves to shared memory for the rest of the visit and
+                // the topic the step could not place is inserted there
+                nt = MAXNT;
+#pragma unroll
+                for (int g = 0; g < MAXNT; ++g) {
+                  smem_u32(SV + (g << 5) + lane) = sv[g];
+                  smem_f32(WT + (g << 5) + lane) = wt[g];
+                }
+                if (lane < MAXNT) smem_u32(BD + lane) = (uint32_t)bnd;
+                __syncwarp();
+                wide_insert(c, nt, newt, TABLES_IN_SMEM ? smem_f32(c.tab + newt) : __ldg(p.invden + newt));
+                wide = true;
+              }
             }
             if (lane == t) new_l = newt;
           }
@@ -764,7 +800,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
         if (MODE != MODE_FROZEN) {
           for (int j = lane; j < c.bmw; j += 32) smem_u32(c.bm + j) = 0u;
           __syncwarp();
-          if (!WIDE) {
+          if (!wide) {
 #pragma unroll
             for (int g = 0; g < MAXNT; ++g)
               if (sv[g] & 0xffffu) atomicOr(smem_u32_ptr(c.bm + (sv[g] >> 21)), 1u << ((sv[g] >> 16) & 31u));
@@ -781,7 +817,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
                             (p.infer_samples == 0 ? it == iters
                                                   : (it > p.infer_burn_in && (it - p.infer_burn_in) % p.infer_thinning == 0));
           int32_t* acc = MODE == MODE_INFER ? p.infer_acc + (size_t)d * K : nullptr;  // this warp owns document d
-          if (!WIDE) {
+          if (!wide) {
 #pragma unroll
             for (int g = 0; g < MAXNT; ++g)
               if (sv[g] & 0xffffu) {

@@ -14,11 +14,15 @@
 
 namespace b200lda {
 
-__global__ void k_topic_tables(int K, const int32_t* __restrict__ nk, const float* __restrict__ alpha_f,
-                               float vbeta, float* __restrict__ invden, float* __restrict__ ab) {
+// nk_delta (may be null): this shard's topic-total moves since the sweep started (LIVE mode
+// rebuilds the tables several times per sweep from the counts as they stand).
+__global__ void k_topic_tables(int K, const int32_t* __restrict__ nk, const int32_t* __restrict__ nk_delta,
+                               const float* __restrict__ alpha_f, float vbeta, float* __restrict__ invden,
+                               float* __restrict__ ab) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  const float inv = __fdiv_rn(1.0f, fadd((float)nk[k], vbeta));
+  const int n = nk[k] + (nk_delta ? nk_delta[k] : 0);
+  const float inv = __fdiv_rn(1.0f, fadd((float)n, vbeta));
   invden[k] = inv;
   ab[k] = fmul(alpha_f[k], inv);
 }
@@ -100,7 +104,8 @@ __global__ void k_form_delta(size_t VK, int K, const int32_t* __restrict__ after
 }
 
 // nwk[i] = before[i] + exchange[i];  nk[k] += exchange[VK + k];  nk_delta = 0
-__global__ void k_apply_delta(size_t VK, int K, int32_t* __restrict__ nwk, const int32_t* __restrict__ before,
+// nwk and before may be the SAME buffer (DEFERRED mode applies the sum in place): no __restrict__ on them.
+__global__ void k_apply_delta(size_t VK, int K, int32_t* nwk, const int32_t* before,
                               const int32_t* __restrict__ exchange, int32_t* __restrict__ nk,
                               int32_t* __restrict__ nk_delta) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;

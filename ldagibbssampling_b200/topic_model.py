@@ -109,7 +109,13 @@ class ParallelTopicModel:
         self.optimizeInterval = int(n)
 
     def setNumThreads(self, n: int):
-        self.numThreads = max(1, int(n))
+        """n AD-LDA shards (= n GPUs). The reference calls it AFTER addInstances
+        (cmu_ron/TrainAndPredict.java:162-164): a change re-shards the documents at the next
+        estimate(), keeping the chain state."""
+        n = max(1, int(n))
+        if n != self.numThreads:
+            self._dirty = True
+        self.numThreads = n
 
     def setRandomSeed(self, seed: int):
         self.randomSeed = int(seed)
@@ -298,8 +304,13 @@ class ParallelTopicModel:
         self._push_assignments_to_data()
 
     def _pull_assignments(self):
-        if self._samplers and not self.distributed:
-            self._z_host = np.concatenate([s.assignments() for s in self._samplers]) if self._samplers else None
+        """Global z (document order) of the chain as it stands, before the device state is rebuilt."""
+        if not self._samplers:
+            return
+        local = np.concatenate([s.assignments() for s in self._samplers])
+        if self.distributed:
+            local = _all_gather_ragged(local, self._samplers[0].device, self.process_group)
+        self._z_host = local
 
     def _push_assignments_to_data(self):
         """Writes z back into every TopicAssignment.topicSequence so `data` consumers
@@ -422,6 +433,25 @@ class TopicInferencer:
         np.cumsum(lens, out=doc_ptr[1:])
         tok = np.concatenate(docs).astype(np.int32) if len(docs) and doc_ptr[-1] > 0 else np.zeros(0, np.int32)
         return m._samplers[0].infer(doc_ptr, tok, numIterations, thinning, burnIn, self.randomSeed)
+
+
+def _all_gather_ragged(local: np.ndarray, device: int, group) -> np.ndarray:
+    """Concatenation over ranks (rank order = document order) of per-rank int32 arrays of different
+    lengths: sizes first, then one padded all_gather on the rank's device."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(local)], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(x.item()) for x in sizes]
+    pad = max(max(sizes), 1)
+    mine = torch.zeros(pad, dtype=torch.int32, device=dev)
+    mine[:len(local)] = torch.from_numpy(np.ascontiguousarray(local, np.int32)).to(dev)
+    parts = [torch.empty(pad, dtype=torch.int32, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return np.concatenate([p[:n].cpu().numpy() for p, n in zip(parts, sizes)])
 
 
 def _fmt(x: float) -> str:

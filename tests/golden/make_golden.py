@@ -103,9 +103,46 @@ def c1():
               open(os.path.join(HERE, "c1_ll_trajectory.json"), "w"), indent=1)
 
 
+def _c4s_run(args):
+    threads, seed, marks = args
+    import bench_corpus as BC
+    dp, tok, V, K = BC.cpu_sample("c4", 20000)
+    z0 = O.init_z(len(tok), K, 7)
+    m = O.MalletModel(K, 0.1 * K, 0.01, seed=seed, threads=threads)
+    m.add_instances(dp, tok, V, z_init=z0)
+    done, row = 0, []
+    for mk in marks:
+        m.estimate(mk - done)
+        done = mk
+        row.append(m.model_log_likelihood() / len(tok))
+    m.close()
+    return threads, seed, row
+
+
+def c4s():
+    """C4-SHAPED sample both sides can run (20 000 documents of BASELINE.json config 4's generator,
+    V = 141 000, K = 1000, alpha_k = 0.1, beta = 0.01 - the sample bench.py's CPU leg uses): LL/token of
+    the Mallet-faithful oracle with 1, 2 and 4 worker threads at sweeps 25, 50, 100, 200 for 3 seeds
+    each, from a shared Philox init. The GPU chains (LIVE, DEFERRED, 2 and 4 shards) must land
+    within 1 % of every seed of the matching row (tests/test_gpu_ll_parity.py)."""
+    import multiprocessing as mp
+    import bench_corpus as BC
+    marks = [25, 50, 100, 200]
+    dp, tok, V, K = BC.cpu_sample("c4", 20000)
+    z0 = O.init_z(len(tok), K, 7)
+    out = {"workload": "c4 sample", "D": 20000, "V": V, "K": K, "alpha_k": 0.1, "beta": 0.01,
+           "init": "oracle.init_z(N, K, seed=7)", "tokens": int(len(tok)), "sweeps": marks,
+           "ll_init": O.loglik(dp, tok, z0, V, K, 0.1, 0.01, True) / len(tok), "mallet_ll_per_token": {}}
+    for threads in (1, 2, 4):
+        with mp.Pool(3 if threads < 4 else 2) as pool:
+            res = pool.map(_c4s_run, [(threads, seed, marks) for seed in (1, 2, 3)])
+        out["mallet_ll_per_token"][str(threads)] = {str(seed): row for _, seed, row in res}
+        json.dump(out, open(os.path.join(HERE, "c4s_ll_trajectory.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     O.build()
-    which = sys.argv[1:] or ["tiny", "frozen", "c1"]
+    which = sys.argv[1:] or ["tiny", "frozen", "c1", "c4s"]
     for w in which:
-        {"tiny": tiny, "frozen": frozen, "c1": c1}[w]()
+        {"tiny": tiny, "frozen": frozen, "c1": c1, "c4s": c4s}[w]()
         print("wrote", w)

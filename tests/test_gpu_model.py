@@ -24,7 +24,7 @@ def _L():
 def test_golden_frozen_triples(oracle):
     L = _L()
     g = np.load(os.path.join(GOLD, "frozen_triples.npz"))
-    for name in ("k4", "k20", "k100", "k1500"):
+    for name in ("k4", "k20", "k100", "k1500", "k3000"):
         D, V, K = [int(x) for x in g[name + "_meta"]]
         s = L.Sampler(K, V, ALPHA * K, BETA, seed=31, mode=L.MODE_DEFERRED)
         s.load_corpus(g[name + "_doc_ptr"], g[name + "_tok"])
@@ -34,8 +34,9 @@ def test_golden_frozen_triples(oracle):
         s.close()
 
 
-def _run_shards(L, dp, tok, V, K, world, mode, seed, sweeps):
-    """`world` contexts on device 0, exchange buffers summed on the device between begin/end."""
+def _run_shards(L, dp, tok, V, K, world, mode, seed, sweeps, z0=None, marks=None):
+    """`world` contexts on device 0, exchange buffers summed on the device between begin/end.
+    marks: return the global LL/token after those sweep counts instead of the samplers."""
     import torch
     from ldagibbssampling_b200.partition import partition_by_tokens, shard_corpus
     from ldagibbssampling_b200.topic_model import _DevBuf
@@ -46,7 +47,7 @@ def _run_shards(L, dp, tok, V, K, world, mode, seed, sweeps):
         s = L.Sampler(K, V, ALPHA * K, BETA, seed=seed, mode=mode, rank=sh.rank, world_size=world,
                       global_token_offset=sh.token_begin, global_doc_offset=sh.doc_begin)
         s.load_corpus(ldp, ltok)
-        s.init_assignments(None)
+        s.init_assignments(None if z0 is None else z0[sh.token_begin:sh.token_end])
         samplers.append(s)
         ptr, n = s.exchange_buffer()
         assert n == V * K + K
@@ -65,15 +66,27 @@ def _run_shards(L, dp, tok, V, K, world, mode, seed, sweeps):
     allreduce()
     for s in samplers:
         s.counts_sync_end()
-    for _ in range(sweeps):
+    curve = []
+    for it in range(1, (marks[-1] if marks else sweeps) + 1):
         for s in samplers:
             s.sweep_begin()
         allreduce()
         for s in samplers:
             s.sweep_end()
+        if marks and it in marks:
+            doc = sum(s.loglik_parts()[0] for s in samplers)
+            curve.append((doc + samplers[0].loglik_parts()[1]) / len(tok))
     for s in samplers:
         s.synchronize()
+    if marks:
+        for s in samplers:
+            s.close()
+        return curve
     return samplers
+
+
+def _run_shards_marks(L, dp, tok, V, K, world, mode, seed, z0, marks):
+    return _run_shards(L, dp, tok, V, K, world, mode, seed, 0, z0=z0, marks=marks)
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -265,3 +265,33 @@ def test_launch_policy_does_not_change_deferred_results(oracle, monkeypatch):
         assert np.array_equal(s.assignments(), want), f"policy {policy}"
         classes = s.stats()["row_classes"]
     assert classes >= 3
+
+
+def test_row_growing_past_eight_tiles_moves_to_shared_memory(oracle):
+    """Documents of ~300 tokens start a sweep with ~250 distinct topics (8 register tiles) and, at
+    K = 3000 where nearly every draw lands on a topic new to the document, grow past 256 live slots
+    during the visit: the row moves from registers to shared memory mid-visit. Frozen topics and the
+    whole DEFERRED chain stay bit-exact with the oracle, before and after the move."""
+    rng = np.random.default_rng(8)
+    V, K, D = 400, 3000, 24
+    lens = rng.integers(290, 330, D).astype(np.int64)
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z0 = np.empty(int(dp[-1]), np.int32)
+    for d in range(D):  # ~250 distinct topics per document, the rest repeats
+        L = int(lens[d])
+        distinct = rng.choice(K, 250, replace=False)
+        z0[dp[d]:dp[d + 1]] = np.concatenate([distinct, rng.choice(distinct, L - 250)])
+    import ldagibbssampling_b200 as L
+    alpha = 0.5  # alpha K = 1500 against 300 tokens: the prior bucket dominates and the rows grow
+    s = L.Sampler(K, V, alpha * K, BETA, seed=6, mode=L.MODE_DEFERRED)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    assert np.array_equal(s.sample_frozen(None, sweep=2), oracle.spec_frozen(dp, tok, z0, V, K, alpha, BETA, 6, 2))
+    s.sweep(3)
+    want = oracle.spec_sweeps(dp, tok, z0, V, K, alpha, BETA, 6, 1, 3)
+    assert np.array_equal(s.assignments(), want)
+    rp, topic, cnt = s.ndk_csr()
+    assert np.diff(rp).max() > 256  # the rows did outgrow the register path
+    nwk, nk = oracle.count(dp, tok, want, V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
