@@ -102,7 +102,11 @@ typedef struct {
    * these the widest one (the longest documents): its document count, row slots, CTAs */
   int64_t long_docs;
   int32_t long_slot_capacity, long_ctas;
-  int32_t row_classes, reserved1;
+  int32_t row_classes;
+  /* LIVE mode table refresh: rebuilds per sweep used by the last sweep (config table_refresh or
+   * the auto choice), the number of hot words, and the prior rows rebuilt during the last sweep */
+  int32_t table_refresh_last;
+  int64_t hot_words, rows_refreshed_last;
 } b200lda_stats;
 
 /* Message of the calling thread's most recent failure ("" if none). Never NULL. */

@@ -53,7 +53,8 @@ class Stats(C.Structure):
         ("cum_finish_ms", C.c_double), ("cum_tokens_moved", C.c_int64),
         ("cum_prior_bucket", C.c_int64), ("cum_doc_topics", C.c_int64),
         ("long_docs", C.c_int64), ("long_slot_capacity", C.c_int32), ("long_ctas", C.c_int32),
-        ("row_classes", C.c_int32), ("reserved1", C.c_int32),
+        ("row_classes", C.c_int32), ("table_refresh_last", C.c_int32),
+        ("hot_words", C.c_int64), ("rows_refreshed_last", C.c_int64),
     ]
 
     def as_dict(self):

@@ -58,9 +58,9 @@ int fail(int code, const char* fmt, ...) {
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // d_counters: [0] scheduler (long class), [1..3] last sweep {moved, prior draws, nnz sum},
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
-constexpr int kCounters = 12;  // [9..11] sink for the stats of inference passes
+constexpr int kCounters = 16;  // [9..11] sink for the stats of inference passes, [12] prior rows rebuilt in the last sweep
 constexpr int kMaxClasses = 16;
-constexpr int kMaxSegments = 32;  // table rebuilds per LIVE sweep (b200lda_ctx::table_refresh)
+constexpr int kMaxRefresh = 64;  // table rebuilds per LIVE sweep (b200lda_ctx::table_refresh)
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 constexpr int kPartial = 1184;   // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
 
@@ -139,11 +139,15 @@ struct b200lda_ctx {
   int class_streams = 0;  // see launch_sweep
   int max_ctas = 0;       // B200LDA_MAX_CTAS (experiments): cap on the sampling kernel's grid, 0 = none
   int table_refresh = 0;  // LIVE mode: table rebuilds per sweep; 0 = auto (auto_table_refresh)
+  int last_refresh = 1;   // what the last sweep used
 
   // counts + tables
   int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
   float *d_invden = nullptr, *d_ab = nullptr, *d_prior = nullptr, *d_q = nullptr, *d_alpha_f = nullptr;
-  float *d_prior_bg = nullptr, *d_q_bg = nullptr, *d_invden_bg = nullptr;  // sweep-start tables for the background classes
+  int32_t* d_prior_sel = nullptr;   // [V] LIVE mode: which of the two copies of word w's prior row / Q_w is current
+  unsigned* d_row_cursor = nullptr; // next hot word whose row the sampling warps rebuild
+  int32_t* d_hot_words = nullptr;   // [V] words carrying ~90 % of the tokens, [hot_count] valid
+  int hot_count = -1;               // -1: not built for the loaded corpus yet
   double *d_alpha = nullptr, *d_lg_alpha = nullptr;
   std::vector<double> alpha;
   double alpha_sum = 0.0, beta = 0.0;
@@ -155,6 +159,9 @@ struct b200lda_ctx {
   // side streams so the row-width classes of one sweep run concurrently (fork/join by events)
   cudaStream_t side[kMaxClasses] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxClasses] = {}, ev_bulk = nullptr;
+  cudaStream_t refresh_stream = nullptr;  // LIVE mode: the table refreshers run beside the bulk launches
+  cudaEvent_t ev_rfork = nullptr, ev_rjoin = nullptr;
+  bool refresher_pending = false;
   const void* timed_corpus = nullptr;  // corpus whose last sweep left ev_fork / ev_bulk / ev_join to read
   int* d_bad = nullptr;
   void* d_stage = nullptr;
@@ -562,13 +569,16 @@ int build_doc_rows(b200lda_ctx* c, DeviceCorpus& cp) {
 
 // ---- per-sweep pieces ---------------------------------------------------------------------------
 
-int build_tables(b200lda_ctx* c, bool with_delta = false) {
+// use_sel: LIVE training sweeps keep two copies of every word's row (d_prior_sel says which is
+// current); the build writes the other copy and flips. Frozen / inference passes build copy 0.
+int build_tables(b200lda_ctx* c, bool use_sel = false) {
   const float beta_f = (float)c->beta;
   const float vbeta = (float)c->V * beta_f;
-  k_topic_tables<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, with_delta ? c->d_nk_delta : nullptr,
-                                                           c->d_alpha_f, vbeta, c->d_invden, c->d_ab);
+  k_topic_tables<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_alpha_f, vbeta, c->d_invden, c->d_ab);
+  int32_t* sel = use_sel ? c->d_prior_sel : nullptr;
+  if (!use_sel && c->d_prior_sel) CU(cudaMemsetAsync(c->d_prior_sel, 0, sizeof(int32_t) * c->V, c->stream));
   k_prior_rows<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_nwk, c->d_ab, beta_f,
-                                                                            c->layout, c->d_prior, c->d_q);
+                                                                            c->layout, c->d_prior, c->d_q, sel);
   c->launches += 2;
   CU(cudaGetLastError());
   return B200LDA_OK;
@@ -593,6 +603,13 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
   p.prior = c->d_prior;
   p.q = c->d_q;
   p.uniforms = nullptr;
+  p.prior_sel = nullptr;
+  p.hot_words = nullptr;
+  p.hot_count = 0;
+  p.row_cursor = c->d_row_cursor;
+  p.refresh_rows = 0u;
+  p.sampler_warps = 0;
+  p.V = c->V;
   p.layout = c->layout;
   p.K = c->K;
   p.beta_f = (float)c->beta;
@@ -600,44 +617,111 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
   p.sweep = sweep;
   p.global_tok_off = c->cfg.global_token_offset;
   p.stats = c->d_counters + 1;
-  p.stats_cum = c->d_counters + 5;
+  p.refresh_count = c->d_counters + 12;
   return p;
 }
 
-// LIVE mode reads the prior bucket (49 % of the draws at K = 1000, alpha_k = 0.1) from tables built
-// from n_wk / n_k as they stood at the last rebuild. Rebuilt once per sweep the chain mixes like
-// Mallet with twice as many threads (LL/token 4 % behind the single chain at sweep 25 on the
-// C4-shaped 20 k-document sample, profiles/r02_ll_parity.md); 16 rebuilds bring it within 1.5 %.
-// A rebuild streams n_wk and the prefix table once (8 V K bytes) and splits every bulk class
-// into one more launch. Auto: as many rebuilds as cost at most ~5 % of the sweep (a few ms on
-// corpora whose sweeps are that short: nobody waits for them), 16 at most.
+// LIVE mode reads the prior bucket (49 % of the draws at K = 1000, alpha_k = 0.1) from per-word
+// prefix tables. Built once per sweep the chain mixes like Mallet with twice as many threads
+// (LL/token 4 % behind the single chain at sweep 25 on the C4-shaped 20 k-document sample,
+// profiles/r02_ll_parity.md). So in LIVE mode a few CTAs of every bulk launch do not sample but keep
+// rebuilding the rows of the HOT words (those that carry ~90 % of the tokens) from the live counts
+// while the sweep runs (sweep_kernel.cuh: refresher_cta), each `table_refresh` times per sweep in
+// all. A rebuilding warp is busy ~40 us per row (it waits on DRAM for the word's n_wk row), i.e.
+// the refreshers need  rows/s x 40 us  warps.  Auto: up to 16 rebuilds per sweep, as many as 3 % of
+// the grid's CTAs manage (everything a small corpus's idle CTAs manage).
+constexpr double kRefreshRowSeconds = 40.0e-6;
+constexpr double kSweepTokensPerSecond = 3.0e9;
 int auto_table_refresh(const b200lda_ctx* c, const DeviceCorpus& cp) {
-  const double sweep_ms = (double)cp.N / 3.0e6;
-  const double rebuild_ms = 8.0 * (double)c->V * (double)c->K / 5.0e9 + 0.1 * (double)std::max<size_t>(1, cp.classes.size());
-  const double budget_ms = std::max(0.05 * sweep_ms, 5.0 - 0.2 * sweep_ms);
-  return (int)std::max(1.0, std::min(16.0, std::floor(budget_ms / rebuild_ms)));
+  return (c->hot_count > 0 && cp.N > 0) ? 16 : 1;  // the refreshers' share of the grid bounds what is reached (launch_class)
 }
 
-// seg / nseg: the launch covers the seg-th of nseg equal ranges of the class's scheduler chunks
-// (chunks are strided through the longest-first order, so every range is a cross-section).
+// The hot words of the loaded corpus: the most frequent words that together carry 90 % of the
+// tokens (at most V/4 of them). Word frequencies = row sums of n_wk; the threshold comes from a
+// 32-bin log2 histogram on the host.
+int build_hot_words(b200lda_ctx* c) {
+  if (c->hot_count >= 0) return B200LDA_OK;
+  if (!c->d_hot_words) TRY(dev_alloc_t(c, &c->d_hot_words, (size_t)c->V));
+  TRY(ensure_stage(c, sizeof(int32_t) * (size_t)c->V));
+  int32_t* d_cnt = reinterpret_cast<int32_t*>(c->d_stage);
+  k_word_counts<<<grid_for(c, (int64_t)c->V * 32, 256), 256, 0, c->stream>>>(c->V, c->K, c->d_nwk, d_cnt);
+  std::vector<int32_t> cnt((size_t)c->V);
+  CU(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * c->V, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  int64_t mass[33] = {0}, words[33] = {0}, total = 0;
+  for (int32_t v : cnt) {
+    int b = 0;
+    while (b < 32 && (1ll << (b + 1)) <= (int64_t)v) ++b;  // 2^b <= v < 2^(b+1)
+    if (v > 0) {
+      mass[b] += v;
+      words[b] += 1;
+      total += v;
+    }
+  }
+  int threshold = 1;
+  int64_t m = 0, n = 0;
+  for (int b = 32; b >= 0; --b) {
+    if (words[b] == 0) continue;
+    if (n > 0 && (n + words[b] > c->V / 4 || m >= (total * 9) / 10)) break;
+    m += mass[b];
+    n += words[b];
+    threshold = (int)std::min<int64_t>(1ll << b, 0x7fffffff);
+  }
+  CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  k_hot_words<<<(c->V + 255) / 256, 256, 0, c->stream>>>(c->V, d_cnt, threshold, c->d_hot_words, c->d_bad);
+  c->launches += 2;
+  int h = 0;
+  CU(cudaMemcpyAsync(&h, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->hot_count = h;
+  return B200LDA_OK;
+}
+
 template <int MODE, bool LIVE>
 int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
-                 unsigned long long* counter, cudaStream_t stream, int max_ctas = 0, int seg = 0, int nseg = 1) {
+                 unsigned long long* counter, cudaStream_t stream, int max_ctas = 0, int refresh_passes = 0,
+                 unsigned* cursor = nullptr) {
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
   p.cap_tiles = sh.cap_tiles;
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
-  const int64_t nchunks = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
-  p.chunk_begin = (unsigned long long)(nchunks * seg / nseg);
-  p.chunk_end = (unsigned long long)(nchunks * (seg + 1) / nseg);
-  if (p.chunk_end <= p.chunk_begin) return B200LDA_OK;
-  const int64_t warps_needed = (int64_t)(p.chunk_end - p.chunk_begin);
+  const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
   if (c->max_ctas > 0) max_ctas = max_ctas > 0 ? std::min(max_ctas, c->max_ctas) : c->max_ctas;
   const int grid_cap = max_ctas > 0 ? std::min(max_ctas, sh.ctas) : sh.ctas;
-  const int ctas = (int)std::max<int64_t>(
+  int ctas = (int)std::max<int64_t>(
       1, std::min<int64_t>(grid_cap, (warps_needed + sh.warps_per_cta - 1) / sh.warps_per_cta));
+  if (LIVE && MODE == MODE_UPDATE && refresh_passes > 0 && c->hot_count > 0 && c->corp.N > 0) {
+    // This launch's share of the sweep's row rebuilds and the refresher CTAs (8 warps each) that
+    // keep up with it. A refresher CTA takes the place of a sampler CTA, so its cost is its share
+    // of the grid: the automatic choice spends 3 % of the CTAs and lets the refreshers do what
+    // they can of 16 passes; an explicit table_refresh sizes them to reach it (a quarter of the
+    // grid at most). A sampling grid that leaves half the GPU empty (small corpora) has room.
+    const bool automatic = c->table_refresh == 0;
+    const double share = (double)(end - begin) / (double)std::max<int64_t>(1, c->corp.D);
+    const double rows = (double)refresh_passes * (double)c->hot_count * share;
+    const double launch_s = share * (double)c->corp.N / kSweepTokensPerSecond;
+    const double row_s = kRefreshRowSeconds * std::max(1.0, (double)c->K / 1000.0);
+    const int want = (int)std::ceil(rows * row_s / std::max(launch_s, 1e-6) / 8.0);
+    const int room = grid_cap - ctas;
+    const int cap = automatic ? std::max(room, (grid_cap * 3 + 99) / 100) : std::max(room, grid_cap / 4);
+    const int refreshers = std::max(1, std::min(want, cap));
+    if (rows >= 1.0 && grid_cap - refreshers >= 1) {
+      SweepParams pr = p;
+      pr.refresh_rows = (unsigned)std::min(rows, 4.0e9);
+      pr.row_cursor = cursor;
+      ctas = std::min(ctas, grid_cap - refreshers);
+      pr.sampler_warps = ctas * sh.warps_per_cta;
+      CU(cudaEventRecord(c->ev_rfork, stream));  // after the previous class's samplers, beside this class's
+      CU(cudaStreamWaitEvent(c->refresh_stream, c->ev_rfork, 0));
+      k_prior_refresher<<<refreshers, 256, 0, c->refresh_stream>>>(pr, (unsigned long long)warps_needed);
+      c->launches += 1;
+      c->refresher_pending = true;
+      CU(cudaGetLastError());
+    }
+  }
   const int threads = sh.warps_per_cta * 32;
 #define B200LDA_LAUNCH(TS, RC) k_gibbs_sweep<MODE, LIVE, TS, RC><<<ctas, threads, sh.smem, stream>>>(p)
   switch (sh.rc * 2 + (sh.tables_in_smem ? 1 : 0)) {
@@ -702,66 +786,42 @@ void retune_background(b200lda_ctx* c, DeviceCorpus& cp) {
 // context's stream with a reduced grid, and the sweep joins them: a long document's latency is
 // hidden behind the bulk, and its CTAs do not take bulk CTAs' register-file slots on every SM.
 template <int MODE, bool LIVE>
-int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p_in, int segments = 1) {
+int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p, int refresh_passes = 0) {
   retune_background(c, cp);
-  SweepParams p = p_in;
   if (MODE != MODE_INFER) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+  if (MODE == MODE_UPDATE) CU(cudaMemsetAsync(c->d_counters + 12, 0, sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
+  CU(cudaMemsetAsync(c->d_row_cursor, 0, sizeof(unsigned) * kMaxClasses, c->stream));
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
-  segments = std::max(1, std::min(segments, kMaxSegments));
-  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses * kMaxSegments, c->stream));
+  if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
   // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = the policy above (default);
   // 1 = everything in sequence; 2 = every class forked at full size.
   std::vector<bool> forked(n, false);
-  bool any_fork = false;
   for (size_t i = 0; i + 1 < n; ++i) {
-    forked[i] = c->class_streams == 2 || (c->class_streams == 0 && cp.classes[i].side_ctas > 0);
-    any_fork = any_fork || forked[i];
-  }
-  SweepParams pbg = p;  // tables the background classes read for the whole sweep
-  if (segments > 1 && any_fork) {
-    // The bulk's tables are rebuilt between segments while the background classes are still
-    // running: those keep a copy of the sweep-start tables.
-    const size_t pw = (size_t)c->V * c->layout.stride;
-    if (!c->d_prior_bg) {
-      TRY(dev_alloc_t(c, &c->d_prior_bg, pw));
-      TRY(dev_alloc_t(c, &c->d_q_bg, (size_t)c->V));
-      TRY(dev_alloc_t(c, &c->d_invden_bg, (size_t)2 * c->K));
-    }
-    CU(cudaMemcpyAsync(c->d_prior_bg, c->d_prior, sizeof(float) * pw, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_q_bg, c->d_q, sizeof(float) * c->V, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_invden_bg, c->d_invden, sizeof(float) * c->K, cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_invden_bg + c->K, c->d_ab, sizeof(float) * c->K, cudaMemcpyDeviceToDevice, c->stream));
-    pbg.prior = c->d_prior_bg;
-    pbg.q = c->d_q_bg;
-    pbg.invden = c->d_invden_bg;
-    pbg.ab = c->d_invden_bg + c->K;
-  }
-  if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
-  for (size_t i = 0; i + 1 < n; ++i) {
-    if (!forked[i]) continue;
     const DeviceCorpus::DocClass& dc = cp.classes[i];
-    cudaStream_t st = c->side[i];
-    CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-    TRY((launch_class<MODE, LIVE>(c, pbg, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments, st,
-                                  c->class_streams == 0 ? dc.side_ctas : 0)));
-    CU(cudaEventRecord(c->ev_join[i], st));
+    const bool fork = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
+    forked[i] = fork;
+    cudaStream_t st = fork ? c->side[i] : c->stream;
+    if (fork) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+    TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i, st,
+                                  c->class_streams == 0 ? dc.side_ctas : 0, fork ? 0 : refresh_passes,
+                                  c->d_row_cursor + i)));
+    if (fork) CU(cudaEventRecord(c->ev_join[i], st));
   }
-  for (int seg = 0; seg < segments; ++seg) {
-    if (seg > 0) TRY(build_tables(c, true));  // LIVE: prior rows and 1/(n_k + V beta) from the counts as they stand
-    for (size_t i = 0; i < n; ++i) {
-      if (i + 1 < n && forked[i]) continue;
-      const DeviceCorpus::DocClass& dc = cp.classes[i];
-      TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments + seg, c->stream, 0,
-                                    seg, segments)));
-    }
-  }
+  TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
+                                c->d_sched + (n - 1), c->stream, 0, refresh_passes, c->d_row_cursor + (n - 1))));
   if (n > 1) {
     CU(cudaEventRecord(c->ev_bulk, c->stream));
     c->timed_corpus = &cp;
   }
   for (size_t i = 0; i + 1 < n; ++i)
     if (forked[i]) CU(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+  if (c->refresher_pending) {  // the refreshers leave right after their samplers: join them
+    CU(cudaEventRecord(c->ev_rjoin, c->refresh_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_rjoin, 0));
+    c->refresher_pending = false;
+  }
   return B200LDA_OK;
 }
 
@@ -865,8 +925,8 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->layout = make_layout(c->K);
   if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
   if (const char* e = std::getenv("B200LDA_MAX_CTAS")) c->max_ctas = atoi(e);
-  c->table_refresh = std::max(0, std::min((int)cfg->table_refresh, kMaxSegments));
-  if (const char* e = std::getenv("B200LDA_TABLE_REFRESH")) c->table_refresh = std::max(0, std::min(atoi(e), kMaxSegments));
+  c->table_refresh = std::max(0, std::min((int)cfg->table_refresh, kMaxRefresh));
+  if (const char* e = std::getenv("B200LDA_TABLE_REFRESH")) c->table_refresh = std::max(0, std::min(atoi(e), kMaxRefresh));
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
   int rc = B200LDA_OK;
   auto bail = [&](int code) {
@@ -884,7 +944,10 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   {
     int lo = 0, hi = 0;  // wide-row classes get the higher priority: their chains are the critical path
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    bool ok = cudaEventCreate(&c->ev_fork) == cudaSuccess && cudaEventCreate(&c->ev_bulk) == cudaSuccess;
+    bool ok = cudaEventCreate(&c->ev_fork) == cudaSuccess && cudaEventCreate(&c->ev_bulk) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_rfork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_rjoin, cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&c->refresh_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
     for (int i = 0; i < kMaxClasses && ok; ++i)
       ok = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaEventCreate(&c->ev_join[i]) == cudaSuccess;
@@ -896,12 +959,20 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_nk_delta, c->K)) || (rc = dev_alloc_t(c, &c->d_invden, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
-      (rc = dev_alloc_t(c, &c->d_prior, (size_t)c->V * c->layout.stride)) || (rc = dev_alloc_t(c, &c->d_q, c->V)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses * kMaxSegments)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_prior, (size_t)(cfg->mode == B200LDA_MODE_LIVE ? 2 : 1) * c->V * c->layout.stride)) ||
+      (rc = dev_alloc_t(c, &c->d_q, (size_t)(cfg->mode == B200LDA_MODE_LIVE ? 2 : 1) * c->V)) ||
+      (rc = dev_alloc_t(c, &c->d_row_cursor, kMaxClasses)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
     if ((rc = dev_alloc_t(c, &c->d_nwk_b, VK))) return bail(rc);
+  if (cfg->mode == B200LDA_MODE_LIVE) {
+    if ((rc = dev_alloc_t(c, &c->d_prior_sel, c->V))) return bail(rc);
+    if (cudaMemsetAsync(c->d_prior_sel, 0, sizeof(int32_t) * c->V, c->stream) != cudaSuccess ||
+        cudaMemsetAsync(c->d_row_cursor, 0, sizeof(unsigned) * kMaxClasses, c->stream) != cudaSuccess)
+      return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
+  }
   if (multi)
     if ((rc = dev_alloc_t(c, &c->d_exchange, VK + c->K))) return bail(rc);
   if (cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
@@ -928,9 +999,9 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_ab);
   dev_free(c->d_prior);
   dev_free(c->d_q);
-  dev_free(c->d_prior_bg);
-  dev_free(c->d_q_bg);
-  dev_free(c->d_invden_bg);
+  dev_free(c->d_prior_sel);
+  dev_free(c->d_row_cursor);
+  dev_free(c->d_hot_words);
   dev_free(c->d_alpha_f);
   dev_free(c->d_alpha);
   dev_free(c->d_lg_alpha);
@@ -943,6 +1014,9 @@ void b200lda_destroy(b200lda_ctx* c) {
   if (c->d_stage) cudaFree(c->d_stage);
   for (auto& e : c->ev_pool)
     if (e) cudaEventDestroy(e);
+  if (c->ev_rfork) cudaEventDestroy(c->ev_rfork);
+  if (c->ev_rjoin) cudaEventDestroy(c->ev_rjoin);
+  if (c->refresh_stream) cudaStreamDestroy(c->refresh_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_bulk) cudaEventDestroy(c->ev_bulk);
   for (int i = 0; i < kMaxClasses; ++i) {
@@ -969,6 +1043,7 @@ int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
   if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
   if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
   c->assigned = false;
+  c->hot_count = -1;
   DeviceCorpus& cp = c->corp;
   const int64_t N = cp.N;
   if (N > 0) {
@@ -1033,19 +1108,29 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   const bool multi = c->cfg.world_size > 1;
   const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
   const size_t VK = (size_t)c->V * c->K;
+  if (!deferred && c->table_refresh != 1) TRY(build_hot_words(c));  // once per corpus
   TRY(next_event_quad(c));
   CU(cudaEventRecord(c->ev[0], c->stream));
-  TRY(build_tables(c));
+  TRY(build_tables(c, !deferred));
   CU(cudaEventRecord(c->ev[1], c->stream));
   if (deferred || multi)
     CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
   // DEFERRED: read the frozen d_nwk, write moves into the copy d_nwk_b.
   // LIVE:     read and write d_nwk in place (d_nwk_b keeps the sweep-start snapshot if multi).
   SweepParams p = sweep_params(c, c->corp, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
-  if (deferred)
+  if (deferred) {
     TRY((launch_sweep<MODE_UPDATE, false>(c, c->corp, p)));
-  else
-    TRY((launch_sweep<MODE_UPDATE, true>(c, c->corp, p, c->table_refresh > 0 ? c->table_refresh : auto_table_refresh(c, c->corp))));
+  } else {
+    // rows the sampling warps rebuild per token (20-bit fixed point): every word's row is rebuilt
+    // table_refresh times per sweep, the first of them by build_tables above
+    const int refresh = c->table_refresh > 0 ? c->table_refresh : auto_table_refresh(c, c->corp);
+    c->last_refresh = refresh;
+    p.prior_sel = c->d_prior_sel;
+    p.hot_words = c->d_hot_words;
+    p.hot_count = c->hot_count;
+    TRY((launch_sweep<MODE_UPDATE, true>(c, c->corp, p, refresh - 1)));
+  }
+  k_accumulate_stats<<<1, 32, 0, c->stream>>>(c->d_counters + 1, c->d_counters + 5);
   CU(cudaEventRecord(c->ev[2], c->stream));
   if (multi) {
     const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;
@@ -1175,7 +1260,6 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
     // replaces `iterations` launch sets + accumulate passes. Philox keys: sweep = iteration.
     SweepParams p = sweep_params(c, cp, c->d_nwk, nullptr, 0u);  // MODE_INFER: the held-out tokens are not part of n_wk / n_k
     p.stats = c->d_counters + 9;  // inference leaves the training chain's sweep statistics alone
-    p.stats_cum = c->d_counters + 9;
     p.seed = seed;
     p.global_tok_off = 0;
     p.infer_iters = iterations;
@@ -1561,6 +1645,8 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
     out->long_slot_capacity = tail.slot_cap;
     out->long_ctas = tail.ctas;
     out->row_classes = (int32_t)c->corp.classes.size();
+    out->table_refresh_last = c->last_refresh;
+    out->hot_words = std::max(0, c->hot_count);
   }
   if (c->in_sweep) return B200LDA_OK;  // timings of an open sweep are not resolvable yet
   TRY(resolve_events(c));
@@ -1580,6 +1666,7 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->cum_tokens_moved = (int64_t)h[5];
   out->cum_prior_bucket = (int64_t)h[6];
   out->cum_doc_topics = (int64_t)h[7];
+  out->rows_refreshed_last = (int64_t)h[12];
   return B200LDA_OK;
 }
 

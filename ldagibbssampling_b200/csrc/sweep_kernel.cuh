@@ -34,6 +34,7 @@
 // accumulator at every saved iteration.
 #pragma once
 #include "device_common.cuh"
+#include "table_kernels.cuh"
 
 namespace b200lda {
 
@@ -57,6 +58,18 @@ struct SweepParams {
   const float* prior;         // [V * layout.stride]
   const float* q;             // [V]  prior bucket mass per word
   const float* uniforms;      // [N] or nullptr (Philox)
+  // LIVE mode: two copies of every word's prior row and Q_w (copy c of word w at row 2 w + c);
+  // prior_sel[w] = the current copy. Beside a bulk launch runs k_prior_refresher: a few small CTAs
+  // that rebuild refresh_rows rows of the hot words from the live counts, paced by the document
+  // scheduler's progress.
+  int32_t* prior_sel;         // [V] or nullptr (one copy)
+  unsigned* row_cursor;       // rows claimed so far in this launch
+  const int32_t* hot_words;   // [hot_count] the words that carry ~90 % of the tokens: the rows worth rebuilding
+  int hot_count;
+  unsigned refresh_rows;
+  unsigned long long* refresh_count;  // statistics: rows rebuilt
+  int sampler_warps;          // warps of the sampling launch the refreshers run beside
+  int V;
   PriorLayout layout;
   int K;
   int cap_tiles;              // wide class: tiles of the shared-memory row (0 in the register classes)
@@ -66,9 +79,7 @@ struct SweepParams {
   uint32_t sweep;
   int64_t global_tok_off;
   unsigned long long* doc_counter;  // dynamic document scheduler: next chunk index (starts at 0 for each launch)
-  unsigned long long chunk_begin, chunk_end;  // this launch's range of scheduler chunks (a segment of the class)
-  unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens
-  unsigned long long* stats_cum;    // same three, accumulated until b200lda_reset_stats
+  unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens (this pass)
   // MODE_INFER: iterations 1..infer_iters per document (Philox sweep key = iteration); a sample is
   // saved when it > burn_in and (it - burn_in) % thinning == 0, or after the last iteration when
   // no iteration qualifies (infer_samples == 0): acc[d, k] += n_dk.
@@ -201,14 +212,24 @@ struct WarpCtx {
 // per 32-token batch (one lane per token) and, for narrow rows, this lane's entry of the top search
 // level is requested at the start of the token step, before the bucket is known. A draw that lands
 // in the prior bucket then pays one dependent memory access per remaining level only.
-__device__ __forceinline__ const float* prior_row_ptr(const SweepParams& p, uint32_t w) {
-  const char* r = reinterpret_cast<const char*>(p.prior) + (size_t)w * (size_t)(4u * (uint32_t)p.layout.stride);
+// LIVE: rows are rewritten during the sweep (the copy that is not current), so they are read at L2,
+// never through the non-coherent path.
+#ifndef B200LDA_PRIOR_CG
+#define B200LDA_PRIOR_CG 1
+#endif
+template <bool LIVE>
+__device__ __forceinline__ float prior_load(const float* a) { return (LIVE && B200LDA_PRIOR_CG) ? __ldcg(a) : __ldg(a); }
+// rw = the row index: the word (one copy) or 2 word + copy (LIVE: two copies per word)
+__device__ __forceinline__ const float* prior_row_ptr(const SweepParams& p, uint32_t rw) {
+  const char* r = reinterpret_cast<const char*>(p.prior) + (size_t)rw * (size_t)(4u * (uint32_t)p.layout.stride);
   asm volatile("" : "+l"(r));  // opaque: one IMAD.WIDE per token, every level load is an offset from it
   return reinterpret_cast<const float*>(r);
 }
+template <bool LIVE>
 __device__ __forceinline__ float prior_top_entry(const float* prow, const WarpCtx& c) {
-  return (c.top_lane >= 0) ? __ldg(prow + (uint32_t)c.top_lane) : 0.0f;
+  return (c.top_lane >= 0) ? prior_load<LIVE>(prow + (uint32_t)c.top_lane) : 0.0f;
 }
+template <bool LIVE>
 __device__ __forceinline__ int prior_search(const SweepParams& p, const float* prow, int lane, int K, float po, float y,
                                             float delta, float vtop) {
   const float pod = fsub(po, delta);
@@ -221,7 +242,7 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, const float* p
     const int lo = block << 5;
     const int nvalid = min(32, p.layout.size[lev] - lo);
     float v = 0.0f;
-    if (lane < nvalid) v = __ldg(prow + (uint32_t)(p.layout.off[lev] + lo + lane));
+    if (lane < nvalid) v = prior_load<LIVE>(prow + (uint32_t)(p.layout.off[lev] + lo + lane));
     const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
     block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
   }
@@ -229,7 +250,7 @@ __device__ __forceinline__ int prior_search(const SweepParams& p, const float* p
     const int lo = block << 5;
     const int nvalid = min(32, K - lo);
     float v = 0.0f;
-    if (lane < nvalid) v = __ldg(prow + (uint32_t)(lo + lane));
+    if (lane < nvalid) v = prior_load<LIVE>(prow + (uint32_t)(lo + lane));
     const unsigned b = __ballot_sync(kFullMask, (lane < nvalid) && (v > s));
     block = lo + (b ? (__ffs(b) - 1) : (nvalid - 1));
   }
@@ -315,9 +336,9 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
                                           int (&nv)[MAXNT], int& nt, int bnd, uint32_t tok_addr) {
   constexpr bool EXCL = MODE != MODE_INFER;
   const int lane = c.lane;
-  const uint4 ta = lds_u128(tok_addr);       // word, old topic, uniform, Q_w
+  const uint4 ta = lds_u128(tok_addr);       // prior row index (LIVE: 2 word + copy, else word), old topic, uniform, Q_w
   const uint4 tb = lds_u128(tok_addr + 16);  // invden[o], ab[o] (0 in inference), P_w[o], next token's word
-  const uint32_t w = ta.x;
+  const uint32_t w = LIVE ? ta.x >> 1 : ta.x;
   const int o = (int)ta.y;
   const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
   const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
@@ -329,10 +350,10 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
 #pragma unroll
   for (int g = 0; g < NT; ++g)  // a dead slot reads a valid cell; its weight is +0
     nvn[g] = count_load<LIVE>(nrow_next + (sv[g] >> 16));
-  const float* prow = prior_row_ptr(p, w);
+  const float* prow = prior_row_ptr(p, ta.x);
   constexpr bool kTopEarly = NT <= TE;  // request the prior's top level before the bucket is known
   float vtop = 0.0f;
-  if (kTopEarly) vtop = prior_top_entry(prow, c);
+  if (kTopEarly) vtop = prior_top_entry<LIVE>(prow, c);
   // a live slot of topic o reads (o << 16) + count with 1 <= count <= 0xffff
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
   // Lane-strided prefix: the lane sums its own slots tile by tile (from +0), ONE warp scan runs over
@@ -374,8 +395,8 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
     if (b != 0u && (pk & 0xffffu) != 0u && pk != okey) newt = (int)(pk >> 16);
   } else {
     ++c.st_prior;
-    if (!kTopEarly) vtop = prior_top_entry(prow, c);
-    newt = prior_search(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, vtop);
+    if (!kTopEarly) vtop = prior_top_entry<LIVE>(prow, c);
+    newt = prior_search<LIVE>(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, vtop);
   }
 
   if (MODE != MODE_FROZEN && __any_sync(kFullMask, newt != o)) {
@@ -504,11 +525,11 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
   const int lane = c.lane;
   const int SV = c.row, WT = c.row + 32 * c.capT, PS = c.row + 64 * c.capT, BD = c.row + 96 * c.capT;
   const uint4 ta = smem_u128(tok);
-  const uint32_t w = ta.x;
+  const uint32_t w = LIVE ? ta.x >> 1 : ta.x;
   const int o = (int)ta.y;
   const float u = __uint_as_float(ta.z), qw = __uint_as_float(ta.w);
   const int32_t* nrow = p.nwk_read + (size_t)w * (size_t)(uint32_t)c.K;
-  const float* prow = prior_row_ptr(p, w);
+  const float* prow = prior_row_ptr(p, ta.x);
   const uint4 tb = smem_u128(tok + 4);
   const float inv_o = __uint_as_float(tb.x), delta = __uint_as_float(tb.y);
   const uint32_t okey = ((uint32_t)o << 16) + 1u;
@@ -567,7 +588,7 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
     }
   } else {
     ++c.st_prior;
-    newt = prior_search(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, prior_top_entry(prow, c));
+    newt = prior_search<LIVE>(p, prow, lane, c.K, __uint_as_float(tb.z), fsub(x, A), delta, prior_top_entry<LIVE>(prow, c));
   }
 
   if (MODE != MODE_FROZEN && newt != o) {
@@ -593,6 +614,52 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
     count_moves(p, c, write_row<LIVE>(p, nrow, (int)w, c.K), o, newt);
   }
   return newt;
+}
+
+// LIVE mode table refresh: a small kernel launched on a side stream right before a bulk sampling
+// launch, whose grid is that many CTAs short of filling the GPU. Each warp claims the
+// next row index, waits (bounded sleeps) until the samplers have completed that fraction of the
+// launch's document chunks (read off the scheduler counter: every sampler warp's next fetch says
+// its previous chunk is complete), rebuilds the prior row of the hot word in turn from the live
+// counts into the copy that is not current and makes it current. It only READS the scheduler
+// counter, leaves as soon as the samplers have finished, and gives up when the counter has not
+// moved for ~20 ms (the samplers are not running beside it): no sampler ever waits for it and it
+// never waits unboundedly for them. Readers picked a copy through prior_sel before reading; the copy
+// they read stays untouched until the word's NEXT rebuild, a full pass over the hot list later.
+__global__ void __launch_bounds__(256, 8) k_prior_refresher(const SweepParams p, unsigned long long nchunks) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long sampler_warps = (unsigned long long)p.sampler_warps;
+  for (;;) {
+    unsigned idx = 0;
+    if (lane == 0) idx = atomicAdd(p.row_cursor, 1u);
+    idx = __shfl_sync(kFullMask, idx, 0);
+    if (idx >= p.refresh_rows) return;
+    unsigned long long seen = ~0ull;
+    for (int idle = 0;;) {
+      unsigned long long done = 0;
+      if (lane == 0) done = *reinterpret_cast<volatile unsigned long long*>(p.doc_counter);
+      done = __shfl_sync(kFullMask, done, 0);
+      idle = done == seen ? idle + 1 : 0;
+      seen = done;
+      if (idle > 10000) return;
+      done = done > sampler_warps ? done - sampler_warps : 0ull;
+      if (done >= nchunks) return;  // the samplers are done: nothing left to refresh for
+      if (done * (unsigned long long)p.refresh_rows >= (unsigned long long)idx * nchunks) break;
+      __nanosleep(2000);
+    }
+    const unsigned w = (unsigned)__ldg(p.hot_words + idx % (unsigned)p.hot_count);
+    const int copy = 1 - __ldcg(p.prior_sel + w);
+    const size_t rw = 2 * (size_t)w + (size_t)copy;
+    float* out = const_cast<float*>(p.prior) + rw * (size_t)p.layout.stride;
+    const float Q = build_prior_row<true>(p.K, p.nwk_read + (size_t)w * (size_t)p.K, p.ab, p.beta_f, p.layout, out, lane);
+    if (lane == 0) const_cast<float*>(p.q)[rw] = Q;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      *reinterpret_cast<volatile int32_t*>(p.prior_sel + w) = copy;
+      atomicAdd(p.refresh_count, 1ull);
+    }
+  }
 }
 
 template <int MODE, bool LIVE, bool TABLES_IN_SMEM, int ROWCLASS>
@@ -650,9 +717,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   const unsigned long long nchunks = (ndocs + (unsigned long long)p.doc_chunk - 1) / (unsigned long long)p.doc_chunk;
   for (;;) {
     unsigned long long ci = 0;
-    if (lane == 0) ci = p.chunk_begin + atomicAdd(p.doc_counter, 1ull);
+    if (lane == 0) ci = atomicAdd(p.doc_counter, 1ull);
     ci = __shfl_sync(kFullMask, ci, 0);
-    if (ci >= p.chunk_end) break;
+    if (ci >= nchunks) break;
 
     for (unsigned long long di = ci; di < ndocs; di += nchunks) {
       // the document's header, read by lane 0 and broadcast: warp-uniform for the compiler too
@@ -728,8 +795,10 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
               u_l = u24(token_random(p.seed, (uint64_t)(p.global_tok_off + i), sweep_key, 0u).x);
             }
           }
-          const float q_l = valid ? __ldg(p.q + w_l) : 0.0f;
-          const float po_l = valid ? __ldg(p.prior + (size_t)w_l * p.layout.stride + o_l) : 0.0f;  // P_w[o]
+          uint32_t rw_l = (uint32_t)w_l;  // the word's current copy of its prior row / Q_w
+          if (LIVE) rw_l = 2u * (uint32_t)w_l + (valid ? (uint32_t)__ldcg(p.prior_sel + w_l) : 0u);
+          const float q_l = valid ? prior_load<LIVE>(p.q + rw_l) : 0.0f;
+          const float po_l = valid ? prior_load<LIVE>(p.prior + (size_t)rw_l * p.layout.stride + o_l) : 0.0f;  // P_w[o]
           const float inv_l = TABLES_IN_SMEM ? smem_f32(c.tab + o_l) : __ldg(p.invden + o_l);
           float dl_l = 0.0f;  // inference: nothing of the document is in the table
           if (MODE != MODE_INFER) dl_l = TABLES_IN_SMEM ? smem_f32(c.tab + K + o_l) : __ldg(p.ab + o_l);
@@ -739,7 +808,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
           int wn_l = __shfl_down_sync(kFullMask, w_l, 1);
           if (lane + 1 >= cnt) wn_l = w_l;
           __syncwarp();  // the previous batch has been consumed
-          smem_u128(c.batch + 8 * lane) = make_uint4((uint32_t)w_l, (uint32_t)o_l, __float_as_uint(u_l), __float_as_uint(q_l));
+          smem_u128(c.batch + 8 * lane) = make_uint4(rw_l, (uint32_t)o_l, __float_as_uint(u_l), __float_as_uint(q_l));
           smem_u128(c.batch + 8 * lane + 4) =
               make_uint4(__float_as_uint(inv_l), __float_as_uint(dl_l), __float_as_uint(po_l), (uint32_t)wn_l);
           __syncwarp();
@@ -856,18 +925,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
     }
   }
   if (lane == 0) {
-    if (st_moved) {
-      atomicAdd(p.stats + 0, st_moved);
-      atomicAdd(p.stats_cum + 0, st_moved);
-    }
-    if (st_prior) {
-      atomicAdd(p.stats + 1, st_prior);
-      atomicAdd(p.stats_cum + 1, st_prior);
-    }
-    if (st_nnz) {
-      atomicAdd(p.stats + 2, st_nnz);
-      atomicAdd(p.stats_cum + 2, st_nnz);
-    }
+    if (st_moved) atomicAdd(p.stats + 0, st_moved);
+    if (st_prior) atomicAdd(p.stats + 1, st_prior);
+    if (st_nnz) atomicAdd(p.stats + 2, st_nnz);
   }
 }
 

@@ -14,51 +14,104 @@
 
 namespace b200lda {
 
-// nk_delta (may be null): this shard's topic-total moves since the sweep started (LIVE mode
-// rebuilds the tables several times per sweep from the counts as they stand).
-__global__ void k_topic_tables(int K, const int32_t* __restrict__ nk, const int32_t* __restrict__ nk_delta,
-                               const float* __restrict__ alpha_f, float vbeta, float* __restrict__ invden,
-                               float* __restrict__ ab) {
+__global__ void k_topic_tables(int K, const int32_t* __restrict__ nk, const float* __restrict__ alpha_f,
+                               float vbeta, float* __restrict__ invden, float* __restrict__ ab) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  const int n = nk[k] + (nk_delta ? nk_delta[k] : 0);
-  const float inv = __fdiv_rn(1.0f, fadd((float)n, vbeta));
+  const float inv = __fdiv_rn(1.0f, fadd((float)nk[k], vbeta));
   invden[k] = inv;
   ab[k] = fmul(alpha_f[k], inv);
 }
 
-// One warp per word (grid-stride): coalesced 128-byte reads of the n_wk row, tile scan, coalesced
-// writes of the prefix row, then the upper search levels by sub-sampling the level below.
+// One word's prior row: coalesced 128-byte reads of the n_wk row, tile scan, coalesced writes of
+// the prefix row, then the upper search levels by sub-sampling the level below. Warp-collective.
+// CG: the counts are live (other warps move them with atomics): read them at L2.
+template <bool CG>
+__device__ __forceinline__ float build_prior_row(int K, const int32_t* row, const float* __restrict__ ab, float beta_f,
+                                                 const PriorLayout& L, float* out, int lane) {
+  // Four tiles per round: their loads are in flight together and their scans are independent, so a
+  // row costs K/128 memory latencies, not K/32 (the rows of rare words come from DRAM). The
+  // arithmetic is the oracle's: Kogge-Stone inside a tile, tiles chained by carry + x.
+  constexpr int G = 4;
+  float carry = 0.0f;
+  for (int base = 0; base < K; base += 32 * G) {
+    float b[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int k = base + 32 * j + lane;
+      b[j] = 0.0f;
+      if (k < K) b[j] = fmul(fadd((float)(CG ? max(__ldcg(row + k), 0) : row[k]), beta_f), __ldg(ab + k));
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) b[j] = warp_scan_inclusive(b[j], lane);
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int k = base + 32 * j + lane;
+      if (base + 32 * j < K) {  // uniform
+        const float P = fadd(carry, b[j]);
+        if (k < K) {
+          if (CG) __stcs(out + L.off[0] + k, P); else out[L.off[0] + k] = P;
+        }
+        carry = __shfl_sync(kFullMask, P, 31);
+      }
+    }
+  }
+  __syncwarp();
+  for (int lev = 1; lev < L.nlev; ++lev) {
+    const float* lower = out + L.off[lev - 1];
+    float* upper = out + L.off[lev];
+    const int nl = L.size[lev - 1];
+    for (int m = lane; m < L.size[lev]; m += 32) {
+      const int src = min(32 * m + 31, nl - 1);
+      upper[m] = CG ? __ldcg(lower + src) : lower[src];  // CG: never through L1 (the copy was rewritten by this warp)
+    }
+    __syncwarp();
+  }
+  return carry;  // Q_w = the row's last prefix
+}
+
+// One warp per word (grid-stride). sel (may be null): two copies of every row (rows 2 w and 2 w + 1),
+// sel[w] = the current one; the build writes the other copy and flips (no sampling kernel is running).
 __global__ void __launch_bounds__(256)
 k_prior_rows(int V, int K, const int32_t* __restrict__ nwk, const float* __restrict__ ab, float beta_f,
-             PriorLayout L, float* __restrict__ prior, float* __restrict__ q) {
+             PriorLayout L, float* __restrict__ prior, float* __restrict__ q, int32_t* __restrict__ sel) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t gw = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)gridDim.x * warps_per_block;
   for (int64_t w = gw; w < V; w += nw) {
-    const int32_t* row = nwk + (size_t)w * K;
-    float* out = prior + (size_t)w * L.stride;
-    float carry = 0.0f;
-    for (int base = 0; base < K; base += 32) {
-      const int k = base + lane;
-      float b = 0.0f;
-      if (k < K) b = fmul(fadd((float)row[k], beta_f), __ldg(ab + k));
-      b = warp_scan_inclusive(b, lane);
-      const float P = fadd(carry, b);
-      if (k < K) out[L.off[0] + k] = P;
-      carry = __shfl_sync(kFullMask, P, 31);
+    const int copy = sel ? 1 - sel[w] : 0;
+    const size_t rw = sel ? 2 * (size_t)w + (size_t)copy : (size_t)w;  // two interleaved copies per word, or one
+    const float Q = build_prior_row<false>(K, nwk + (size_t)w * K, ab, beta_f, L, prior + rw * L.stride, lane);
+    if (lane == 0) {
+      q[rw] = Q;
+      if (sel) sel[w] = copy;
     }
-    __syncwarp();
-    for (int lev = 1; lev < L.nlev; ++lev) {
-      const float* lower = out + L.off[lev - 1];
-      float* upper = out + L.off[lev];
-      const int nl = L.size[lev - 1];
-      for (int m = lane; m < L.size[lev]; m += 32) upper[m] = lower[min(32 * m + 31, nl - 1)];
-      __syncwarp();
-    }
-    if (lane == 0) q[w] = out[L.off[0] + K - 1];
   }
+}
+
+// cum[0..3) += last[0..3)  (sweep statistics, accumulated until b200lda_reset_stats)
+__global__ void k_accumulate_stats(const unsigned long long* __restrict__ last, unsigned long long* __restrict__ cum) {
+  if (threadIdx.x < 3) cum[threadIdx.x] += last[threadIdx.x];
+}
+
+// Token count of every word (row sums of n_wk), one warp per word.
+__global__ void k_word_counts(int V, int K, const int32_t* __restrict__ nwk, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = gw; w < V; w += nw) {
+    int acc = 0;
+    for (int k = lane; k < K; k += 32) acc += nwk[(size_t)w * K + k];
+    acc = __reduce_add_sync(kFullMask, acc);
+    if (lane == 0) out[w] = acc;
+  }
+}
+// hot[0 .. *n) = the words with at least `threshold` tokens (order unspecified)
+__global__ void k_hot_words(int V, const int32_t* __restrict__ counts, int threshold, int32_t* __restrict__ hot,
+                            int* __restrict__ n) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < V && counts[w] >= threshold) hot[atomicAdd(n, 1)] = w;
 }
 
 // acc[i] += add[i]   (in-process reduction of the shards' exchange buffers)

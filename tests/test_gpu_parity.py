@@ -200,7 +200,7 @@ def test_live_mode_equals_sequential_oracle_when_documents_do_not_interact(oracl
     """LIVE mode updates n_wk in place. Across documents that is a race (by design), but documents
     with disjoint vocabularies never touch the same n_wk rows, so the chain is deterministic and
     must equal the oracle's sequential rendering of LIVE mode (n_wk moves immediately, tables and
-    n_k from the sweep start) bit for bit."""
+    n_k from the sweep start: table_refresh = 1 switches the in-sweep table rebuilds off) bit for bit."""
     import ldagibbssampling_b200 as L
     rng = np.random.default_rng(7)
     K, words_per_doc = 40, 50
@@ -209,12 +209,21 @@ def test_live_mode_equals_sequential_oracle_when_documents_do_not_interact(oracl
     tok = np.concatenate([d * words_per_doc + rng.integers(0, words_per_doc, n) for d, n in enumerate(lens)]).astype(np.int32)
     V = words_per_doc * len(lens)
     z0 = oracle.init_z(len(tok), K, 19)
-    s = _sampler(K, V, seed=19, mode=L.MODE_LIVE)
+    s = _sampler(K, V, seed=19, mode=L.MODE_LIVE, table_refresh=1)
     s.load_corpus(dp, tok)
     s.init_assignments(z0)
     s.sweep(5)
     want = oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 19, 1, 5, live=True)
     assert np.array_equal(s.assignments(), want)
+    # with the rebuilds on (every row 16 times per sweep) the chain differs but the counts stay exact
+    s = _sampler(K, V, seed=19, mode=L.MODE_LIVE, table_refresh=16)
+    s.load_corpus(dp, tok)
+    s.init_assignments(z0)
+    s.sweep(5)
+    z = s.assignments()
+    nwk, nk = oracle.count(dp, tok, z, V, K)
+    assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+    assert oracle.loglik(dp, tok, z, V, K, ALPHA, BETA) > oracle.loglik(dp, tok, z0, V, K, ALPHA, BETA)
 
 
 @pytest.mark.parametrize("K,V,lens", [
