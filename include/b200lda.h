@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B200LDA_ABI_VERSION 1
+#define B200LDA_ABI_VERSION 2
 
 typedef enum {
   B200LDA_OK = 0,
@@ -132,26 +132,31 @@ int b200lda_load_corpus(b200lda_ctx* ctx, int64_t num_docs, const int64_t* doc_p
  * caller's topics (seed-matched init from another sampler, or a restored checkpoint). Builds
  * n_wk, n_k and the sparse n_dk rows. */
 int b200lda_init_assignments(b200lda_ctx* ctx, const int32_t* z);
+/* The same with the topics in the device's own width (K <= 65536): half the bytes over the bus
+ * and no widening pass. For hosts that are not bound to Java's int[] (z must not be NULL). */
+int b200lda_init_assignments_u16(b200lda_ctx* ctx, const uint16_t* z);
 
 /* model.estimate() for n sweeps (setNumIterations(n))      cmu_ron/TrainAndPredict.java:165-166,
  * Single-shard contexts only (world_size == 1); blocks until done.            cmu/…:263,265 */
 int b200lda_sweep(b200lda_ctx* ctx, int32_t n);
 
-/* One AD-LDA sweep of a multi-shard model (setNumThreads(n), cmu_ron/…:164, cmu/…:262; replaces
- * WorkerRunnable.run + ParallelTopicModel.sumTypeTopicCounts):
- *   sweep_begin  enqueues table build + sampling + delta formation;
+/* One AD-LDA sweep of a multi-shard model with the caller's own all-reduce (setNumThreads(n),
+ * cmu_ron/…:164, cmu/…:262; replaces WorkerRunnable.run + ParallelTopicModel.sumTypeTopicCounts):
+ *   sweep_begin  enqueues table build + sampling;
  *   the caller sums the exchange buffer (int32, *count elements, device memory) over all shards
  *     in place — ncclAllReduce(ncclInt32, ncclSum) on the context's stream, or any equivalent;
- *   sweep_end    applies the summed delta to the n_wk / n_k replicas.
+ *     the buffer is the shard's n_wk replica itself ("sweep-start counts + own moves", n_k moves
+ *     in the K-cell tail): nothing is copied to form it;
+ *   sweep_end    turns the sum into the new global counts (sum - (n-1) x sweep-start counts).
  * Neither call synchronises; use b200lda_synchronize. Also valid with world_size == 1. */
 int b200lda_sweep_begin(b200lda_ctx* ctx);
 int b200lda_exchange_buffer(b200lda_ctx* ctx, void** d_buf, int64_t* count);
 int b200lda_sweep_end(b200lda_ctx* ctx);
 /* Once after b200lda_init_assignments on every shard of a multi-shard model (Mallet's
  * sumTypeTopicCounts at start-up): each shard built n_wk / n_k from its own documents only;
- *   counts_sync_begin  copies them into the exchange buffer,
+ *   counts_sync_begin  puts its n_k into the exchange buffer's tail,
  *   the caller sums the exchange buffer over all shards (same all-reduce as per sweep),
- *   counts_sync_end    installs the sum as the n_wk / n_k replica. */
+ *   counts_sync_end    installs the sum as the n_wk / n_k replica and its sweep-start snapshot. */
 int b200lda_counts_sync_begin(b200lda_ctx* ctx);
 int b200lda_counts_sync_end(b200lda_ctx* ctx);
 int b200lda_synchronize(b200lda_ctx* ctx);
@@ -160,9 +165,32 @@ int b200lda_get_stream(b200lda_ctx* ctx, void** stream);
  * process (a JVM after setNumThreads(4), the C++ mirror): sums the exchange buffers (or the
  * hyper-parameter histograms) of the n contexts in place through peer copies. Blocking; the
  * NCCL path above is the fast one. */
+#define B200LDA_NCCL_ID_BYTES 128
 #define B200LDA_BUFFER_EXCHANGE 0
 #define B200LDA_BUFFER_HYPER 1
 int b200lda_group_allreduce(b200lda_ctx** ctxs, int32_t n, int32_t which);
+
+/* NCCL inside the library (loaded at run time; B200LDA_ENODEV when there is no libnccl.so.2).
+ * setNumThreads(n) of the reference (cmu_ron/TrainAndPredict.java:164, cmu/TrainAndPredict.java:262)
+ * = n shards = n GPUs, either
+ *  - one process per GPU: rank 0 calls b200lda_nccl_unique_id, ships the 128 bytes to the other
+ *    ranks by whatever channel the host has, every rank calls b200lda_comm_init on its context;
+ *    from then on b200lda_sweep(ctx, n) runs whole AD-LDA sweeps (collective: every rank calls it)
+ *    and b200lda_group_sync_counts(&ctx, 1) is the start-up count sum; or
+ *  - all n contexts in ONE process (a JVM, the C++ mirror): create them with rank i / world_size n
+ *    on n different devices, call b200lda_group_comm_init once, then b200lda_group_sync_counts
+ *    after the assignments are installed and b200lda_group_sweep(ctxs, n, sweeps) to sample: one
+ *    host thread drives every shard, the all-reduces are grouped (ncclGroupStart/End).
+ * The exchange is in place: every shard all-reduces "sweep-start counts + its own moves" (the
+ * exchange buffer IS its n_wk replica, n_k moves in the K-cell tail) and subtracts (n-1) x the
+ * sweep-start counts; it runs in 8 slabs, slab i applied while slab i+1 is reduced.
+ * Without communicators (several contexts on one device) the group calls fall back to
+ * b200lda_group_allreduce's peer copies. */
+int b200lda_nccl_unique_id(void* id /* B200LDA_NCCL_ID_BYTES */);
+int b200lda_comm_init(b200lda_ctx* ctx, const void* id);
+int b200lda_group_comm_init(b200lda_ctx** ctxs, int32_t n);
+int b200lda_group_sync_counts(b200lda_ctx** ctxs, int32_t n);
+int b200lda_group_sweep(b200lda_ctx** ctxs, int32_t n, int32_t sweeps);
 
 /* Frozen-snapshot parity mode (north star; no Java counterpart): resample every token once
  * against the current counts WITHOUT moving any count. uniforms == NULL uses Philox with the
@@ -187,6 +215,7 @@ int b200lda_loglik_parts(b200lda_ctx* ctx, double* doc_part, double* word_part);
 
 /* model.data.get(d).topicSequence.getFeatures()            cmu_ron/TrainAndPredict.java:135-143 */
 int b200lda_get_assignments(b200lda_ctx* ctx, int32_t* z /* num_tokens, document order */);
+int b200lda_get_assignments_u16(b200lda_ctx* ctx, uint16_t* z /* num_tokens, document order */);
 /* typeTopicCounts / tokensPerTopic (dense)                 used by getInferencer(), cmu_ron/…:169 */
 int b200lda_get_nwk(b200lda_ctx* ctx, int32_t* nwk /* V*K, row-major by word */);
 int b200lda_get_nk(b200lda_ctx* ctx, int32_t* nk /* K */);
@@ -229,8 +258,17 @@ int b200lda_hyper_get(b200lda_ctx* ctx, int32_t* topic_doc_counts /* K*width */,
 int b200lda_optimize_alpha(b200lda_ctx* ctx);
 int b200lda_optimize_beta(b200lda_ctx* ctx);
 
-/* Checkpoint/resume hooks (replaces Java serialisation, cmu_ron/TrainAndPredict.java:179-200):
- * sweep counter continues the Philox stream of a restored chain. */
+/* Checkpoint / resume (replaces the Java serialisation of the trained model,
+ * cmu_ron/TrainAndPredict.java:179-200, and its skip-training-if-the-file-exists path, :215-226):
+ * the chain's whole state as one host blob = header (K, V, D, N, mode, sweep counter, Philox seed,
+ * beta, shard rank/offset, checksum of the loaded doc_ptr / tok_word) + alpha[K] + z[N] (uint16).
+ * set_state needs the SAME corpus loaded (checked by size and checksum); it installs alpha, beta,
+ * the seed and the sweep counter and rebuilds every count from z, so a restored DEFERRED chain
+ * continues bit-identically. Multi-shard models: one blob per shard, then the count sync. */
+int b200lda_state_size(b200lda_ctx* ctx, int64_t* bytes);
+int b200lda_get_state(b200lda_ctx* ctx, void* buf, int64_t bytes);
+int b200lda_set_state(b200lda_ctx* ctx, const void* buf, int64_t bytes);
+/* Sweep counter alone (continues the Philox stream of a chain restored through init_assignments). */
 int b200lda_set_sweep_counter(b200lda_ctx* ctx, int64_t sweeps_done);
 
 int b200lda_get_stats(b200lda_ctx* ctx, b200lda_stats* out);

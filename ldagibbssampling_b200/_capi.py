@@ -71,6 +71,7 @@ SYMBOLS = [
     ("b200lda_destroy", None, [_P]),
     ("b200lda_load_corpus", C.c_int, [_P, C.c_int64, _P, _P]),
     ("b200lda_init_assignments", C.c_int, [_P, _P]),
+    ("b200lda_init_assignments_u16", C.c_int, [_P, _P]),
     ("b200lda_sweep", C.c_int, [_P, C.c_int32]),
     ("b200lda_sweep_begin", C.c_int, [_P]),
     ("b200lda_exchange_buffer", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
@@ -81,10 +82,16 @@ SYMBOLS = [
     ("b200lda_synchronize", C.c_int, [_P]),
     ("b200lda_get_stream", C.c_int, [_P, C.POINTER(_P)]),
     ("b200lda_group_allreduce", C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32]),
+    ("b200lda_nccl_unique_id", C.c_int, [_P]),
+    ("b200lda_comm_init", C.c_int, [_P, _P]),
+    ("b200lda_group_comm_init", C.c_int, [C.POINTER(_P), C.c_int32]),
+    ("b200lda_group_sync_counts", C.c_int, [C.POINTER(_P), C.c_int32]),
+    ("b200lda_group_sweep", C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32]),
     ("b200lda_sample_frozen", C.c_int, [_P, _P, C.c_uint32, _P]),
     ("b200lda_loglik", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("b200lda_loglik_parts", C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("b200lda_get_assignments", C.c_int, [_P, _P]),
+    ("b200lda_get_assignments_u16", C.c_int, [_P, _P]),
     ("b200lda_get_nwk", C.c_int, [_P, _P]),
     ("b200lda_get_nk", C.c_int, [_P, _P]),
     ("b200lda_get_ndk_csr", C.c_int, [_P, _P, _P, _P]),
@@ -101,6 +108,9 @@ SYMBOLS = [
     ("b200lda_hyper_get", C.c_int, [_P, _P, _P]),
     ("b200lda_optimize_alpha", C.c_int, [_P]),
     ("b200lda_optimize_beta", C.c_int, [_P]),
+    ("b200lda_state_size", C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ("b200lda_get_state", C.c_int, [_P, _P, C.c_int64]),
+    ("b200lda_set_state", C.c_int, [_P, _P, C.c_int64]),
     ("b200lda_set_sweep_counter", C.c_int, [_P, C.c_int64]),
     ("b200lda_get_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("b200lda_reset_stats", C.c_int, [_P]),
@@ -183,11 +193,22 @@ class Sampler:
         self.num_docs, self.num_tokens = num_docs, num_tokens
 
     def init_assignments(self, z=None):
+        """z: None (Philox draw on the device), an int32 array (the JVM's layout) or a uint16 array
+        (the device's own width: half the bytes over the bus)."""
+        if z is not None and getattr(z, "dtype", None) == np.uint16:
+            z = np.ascontiguousarray(z)
+            if len(z) != self.num_tokens:
+                raise ValueError("z must have one entry per token")
+            self._check(self._lib.b200lda_init_assignments_u16(self._h, _ptr(z)))
+            return
         if z is not None:
             z = np.ascontiguousarray(z, np.int32)
             if len(z) != self.num_tokens:
                 raise ValueError("z must have one entry per token")
         self._check(self._lib.b200lda_init_assignments(self._h, _ptr(z)))
+
+    def init_assignments_u16_raw(self, z_addr):
+        self._check(self._lib.b200lda_init_assignments_u16(self._h, z_addr))
 
     def init_assignments_raw(self, z_addr):
         self._check(self._lib.b200lda_init_assignments(self._h, z_addr))
@@ -252,10 +273,35 @@ class Sampler:
         self._check(self._lib.b200lda_loglik_parts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def assignments(self):
-        z = np.empty(self.num_tokens, np.int32)
-        self._check(self._lib.b200lda_get_assignments(self._h, _ptr(z)))
+    def assignments(self, dtype=np.int32):
+        z = np.empty(self.num_tokens, dtype)
+        if np.dtype(dtype) == np.uint16:
+            self._check(self._lib.b200lda_get_assignments_u16(self._h, _ptr(z)))
+        else:
+            self._check(self._lib.b200lda_get_assignments(self._h, _ptr(z)))
         return z
+
+    def assignments_u16_raw(self, z_addr):
+        self._check(self._lib.b200lda_get_assignments_u16(self._h, z_addr))
+
+    # -- resumable state ---------------------------------------------------------------------
+    def get_state(self) -> bytes:
+        n = C.c_int64()
+        self._check(self._lib.b200lda_state_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._check(self._lib.b200lda_get_state(self._h, _ptr(buf), n.value))
+        return buf.tobytes()
+
+    def set_state(self, blob: bytes):
+        buf = np.frombuffer(blob, np.uint8)
+        self._check(self._lib.b200lda_set_state(self._h, _ptr(buf), len(buf)))
+
+    # -- NCCL inside the library -----------------------------------------------------------------
+    def comm_init(self, unique_id: bytes):
+        buf = np.frombuffer(unique_id, np.uint8)
+        if len(buf) != NCCL_ID_BYTES:
+            raise ValueError("an NCCL unique id has 128 bytes")
+        self._check(self._lib.b200lda_comm_init(self._h, _ptr(buf)))
 
     def assignments_raw(self, z_addr):
         self._check(self._lib.b200lda_get_assignments(self._h, z_addr))
@@ -358,6 +404,39 @@ def group_allreduce(samplers, which=0):
     rc = lib.b200lda_group_allreduce(arr, len(samplers), which)
     if rc != OK:
         raise B200LDAError(rc, lib.b200lda_last_error().decode())
+
+
+NCCL_ID_BYTES = 128
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = np.zeros(NCCL_ID_BYTES, np.uint8)
+    rc = lib.b200lda_nccl_unique_id(_ptr(buf))
+    if rc != OK:
+        raise B200LDAError(rc, lib.b200lda_last_error().decode())
+    return buf.tobytes()
+
+
+def _group_call(name, samplers, *args):
+    lib = load_library()
+    arr = (C.c_void_p * len(samplers))(*[s._h for s in samplers])
+    rc = getattr(lib, name)(arr, len(samplers), *args)
+    if rc != OK:
+        raise B200LDAError(rc, lib.b200lda_last_error().decode())
+
+
+def group_comm_init(samplers):
+    """One NCCL communicator set for n contexts of this process (one per GPU)."""
+    _group_call("b200lda_group_comm_init", samplers)
+
+
+def group_sync_counts(samplers):
+    _group_call("b200lda_group_sync_counts", samplers)
+
+
+def group_sweep(samplers, sweeps=1):
+    _group_call("b200lda_group_sweep", samplers, sweeps)
 
 
 def device_count() -> int:

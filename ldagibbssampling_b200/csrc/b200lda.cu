@@ -7,6 +7,8 @@
 #include "../../include/b200lda.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -55,10 +57,61 @@ int fail(int code, const char* fmt, ...) {
     if (rc__ != B200LDA_OK) return rc__; \
   } while (0)
 
+// NCCL is loaded at run time (dlopen), never linked: a process that already holds a libnccl (torch
+// bundles its own) keeps using that one, a host without NCCL still runs single-GPU models.
+struct NcclApi {
+  void* handle = nullptr;
+  bool tried = false;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return B200LDA_OK;
+  if (!g_nccl.tried) {
+    g_nccl.tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy the process already uses
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+#define B200LDA_NCCL_SYM(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name))
+      B200LDA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+      B200LDA_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+      B200LDA_NCCL_SYM(CommInitAll, "ncclCommInitAll");
+      B200LDA_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+      B200LDA_NCCL_SYM(AllReduce, "ncclAllReduce");
+      B200LDA_NCCL_SYM(GroupStart, "ncclGroupStart");
+      B200LDA_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+      B200LDA_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef B200LDA_NCCL_SYM
+      if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.AllReduce &&
+          g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString)
+        g_nccl.handle = h;
+    }
+  }
+  if (!g_nccl.handle) return fail(B200LDA_ENODEV, "libnccl.so.2 not found (or too old): multi-GPU exchange needs NCCL");
+  return B200LDA_OK;
+}
+
+#define NCCL(expr)                                                                              \
+  do {                                                                                          \
+    ncclResult_t r__ = (expr);                                                                  \
+    if (r__ != ncclSuccess)                                                                     \
+      return fail(B200LDA_ECUDA, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kExchangeSlabs = 8;  // the all-reduce goes in slabs; slab i is applied while slab i+1 is reduced
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // d_counters: [0] scheduler (long class), [1..3] last sweep {moved, prior draws, nnz sum},
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
-constexpr int kCounters = 16;  // [9..11] sink for the stats of inference passes, [12] prior rows rebuilt in the last sweep
+constexpr int kCounters = 16;  // [13] corpus checksum scratch;  // [9..11] sink for the stats of inference passes, [12] prior rows rebuilt in the last sweep
 constexpr int kMaxClasses = 16;
 constexpr int kMaxRefresh = 64;  // table rebuilds per LIVE sweep (b200lda_ctx::table_refresh)
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
@@ -142,7 +195,13 @@ struct b200lda_ctx {
   int last_refresh = 1;   // what the last sweep used
 
   // counts + tables
-  int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr, *d_exchange = nullptr;
+  // d_nwk: [V K | K] the counts (+ in multi-shard models a K-cell tail: this shard's n_k moves);
+  // d_nwk_b, same shape: DEFERRED single shard: the copy the moves go to; multi-shard: the global
+  // counts of the sweep start (what the in-place exchange subtracts, and DEFERRED's frozen read copy)
+  int32_t *d_nwk = nullptr, *d_nwk_b = nullptr, *d_nk = nullptr, *d_nk_delta = nullptr;
+  ncclComm_t comm = nullptr;        // set by b200lda_comm_init / b200lda_group_comm_init
+  cudaStream_t apply_stream = nullptr;
+  cudaEvent_t ev_slab[kExchangeSlabs] = {}, ev_applied = nullptr;
   float *d_invden = nullptr, *d_ab = nullptr, *d_prior = nullptr, *d_q = nullptr, *d_alpha_f = nullptr;
   int32_t* d_prior_sel = nullptr;   // [V] LIVE mode: which of the two copies of word w's prior row / Q_w is current
   unsigned* d_row_cursor = nullptr; // next hot word whose row the sampling warps rebuild
@@ -171,9 +230,12 @@ struct b200lda_ctx {
   size_t hist_scratch_bytes = 0;
   int32_t* d_hyper = nullptr;  // [(K + 1) * hyper_width] topicDocCounts rows + docLengthCounts row
   int hyper_width = 0, hyper_samples = 0;
+  std::vector<unsigned long long> h_len_hist;  // pack_corpus: host sides of its async copies
+  std::vector<long long> h_len_start;
 
   // state
   bool corpus_loaded = false, assigned = false, in_sweep = false, in_sync = false;
+  bool snapshot_valid = false;  // multi-shard: d_nwk_b holds the global counts of the sweep start
   int64_t sweeps_done = 0, tokens_sampled = 0;
   // per-sweep device timing: 4 events per sweep (begin, tables done, sample done, end), resolved
   // lazily at b200lda_get_stats so no sweep ever synchronises for bookkeeping
@@ -443,8 +505,9 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
   }
   cp.D = num_docs;
   cp.N = N;
+  // The plan needs only doc_ptr: it goes first, and the token stream (the bulk of the bytes) is
+  // copied while the host derives the row-width classes from the length histogram.
   CU(cudaMemcpyAsync(cp.d_doc_ptr, doc_ptr, sizeof(int64_t) * (num_docs + 1), cudaMemcpyHostToDevice, c->stream));
-  if (N > 0) CU(cudaMemcpyAsync(cp.d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
 
   // scratch: [len_hist 65537 | cursor 65537 | len_start 65537 | bad_doc | block sums/offsets ...]
   constexpr int kBins = 65537;
@@ -461,7 +524,8 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
   const long long no_bad = 0x7fffffffffffffffLL;
   CU(cudaMemcpyAsync(d_bad_doc, &no_bad, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
-  std::vector<unsigned long long> h_hist((size_t)kBins, 0);
+  std::vector<unsigned long long>& h_hist = c->h_len_hist;
+  h_hist.assign((size_t)kBins, 0);
   long long bad_doc = no_bad;
   int bad_word = 0;
   if (num_docs > 0) {
@@ -473,23 +537,24 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
   } else {
     CU(cudaMemsetAsync(cp.d_row_ptr, 0, sizeof(int64_t), c->stream));
   }
-  if (N > 0) {
-    k_validate_words<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, cp.d_tok_word, c->d_bad);
-    c->launches += 1;
-  }
   CU(cudaMemcpyAsync(h_hist.data(), d_hist, sizeof(unsigned long long) * kBins, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(&bad_doc, d_bad_doc, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(&bad_word, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // the plan's inputs (a few hundred KB); the token stream has not moved yet
   if (bad_doc != no_bad) {
     const int64_t len = doc_ptr[bad_doc + 1] - doc_ptr[bad_doc];
     if (len < 0) return fail(B200LDA_EINVAL, "doc_ptr is not monotone at document %lld", bad_doc);
     return fail(B200LDA_ERANGE, "document %lld has %lld tokens (limit 65535)", bad_doc, (long long)len);
   }
-  if (bad_word) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
+  if (N > 0) {
+    CU(cudaMemcpyAsync(cp.d_tok_word, tok_word, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+    k_validate_words<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->V, cp.d_tok_word, c->d_bad);
+    c->launches += 1;
+    CU(cudaMemcpyAsync(&bad_word, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
 
-  // host: 64 K bins -> longest document, row capacity, len_ge, class boundaries, order offsets
+  // host (while the token stream is copied): 64 K bins -> longest document, row capacity, len_ge,
+  // class boundaries, order offsets
   int max_len = 0;
   int64_t rows_total = 0;
   for (int L = 0; L < kBins; ++L)
@@ -501,7 +566,8 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
   cp.rows_total = rows_total;
   std::vector<int64_t> len_ge((size_t)max_len + 2, 0);
   for (int L = max_len; L >= 0; --L) len_ge[(size_t)L] = len_ge[(size_t)L + 1] + (int64_t)h_hist[(size_t)L];
-  std::vector<long long> len_start((size_t)kBins, 0);  // documents longer than L come first
+  std::vector<long long>& len_start = c->h_len_start;  // documents longer than L come first; outlives the async copy below
+  len_start.assign((size_t)kBins, 0);
   for (int L = 0; L <= max_len; ++L) len_start[(size_t)L] = len_ge[(size_t)L + 1];
   if (rows_total > cp.cap_rows) {
     dev_free(cp.d_rows);
@@ -516,7 +582,8 @@ int pack_corpus(b200lda_ctx* c, DeviceCorpus& cp, int64_t num_docs, const int64_
   }
   CU(cudaGetLastError());
   TRY(configure_sweep(c, cp, len_ge));
-  CU(cudaStreamSynchronize(c->stream));  // len_start (host vector) must outlive the copy
+  CU(cudaStreamSynchronize(c->stream));  // the caller's buffers are borrowed for the duration of the call only
+  if (bad_word) return fail(B200LDA_ERANGE, "tok_word holds a word id outside [0, %d)", c->V);
   return B200LDA_OK;
 }
 
@@ -955,7 +1022,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   }
   const size_t VK = (size_t)c->V * c->K;
   const bool multi = cfg->world_size > 1;
-  if ((rc = dev_alloc_t(c, &c->d_nwk, VK)) || (rc = dev_alloc_t(c, &c->d_nk, c->K)) ||
+  if ((rc = dev_alloc_t(c, &c->d_nwk, VK + c->K)) || (rc = dev_alloc_t(c, &c->d_nk, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_nk_delta, c->K)) || (rc = dev_alloc_t(c, &c->d_invden, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_ab, c->K)) || (rc = dev_alloc_t(c, &c->d_alpha_f, c->K)) ||
       (rc = dev_alloc_t(c, &c->d_alpha, c->K)) || (rc = dev_alloc_t(c, &c->d_lg_alpha, c->K)) ||
@@ -966,17 +1033,23 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
-    if ((rc = dev_alloc_t(c, &c->d_nwk_b, VK))) return bail(rc);
+    if ((rc = dev_alloc_t(c, &c->d_nwk_b, VK + c->K))) return bail(rc);
   if (cfg->mode == B200LDA_MODE_LIVE) {
     if ((rc = dev_alloc_t(c, &c->d_prior_sel, c->V))) return bail(rc);
     if (cudaMemsetAsync(c->d_prior_sel, 0, sizeof(int32_t) * c->V, c->stream) != cudaSuccess ||
         cudaMemsetAsync(c->d_row_cursor, 0, sizeof(unsigned) * kMaxClasses, c->stream) != cudaSuccess)
       return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
   }
-  if (multi)
-    if ((rc = dev_alloc_t(c, &c->d_exchange, VK + c->K))) return bail(rc);
+  if (multi) {
+    bool ok = cudaStreamCreateWithFlags(&c->apply_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_applied, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMemsetAsync(c->d_nwk_b, 0, sizeof(int32_t) * (VK + c->K), c->stream) == cudaSuccess;
+    for (int i = 0; i < kExchangeSlabs && ok; ++i)
+      ok = cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return bail(fail(B200LDA_ECUDA, "creating the exchange streams failed"));
+  }
   if (cudaMemsetAsync(c->d_nk_delta, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
-      cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream) != cudaSuccess ||
+      cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * (VK + c->K), c->stream) != cudaSuccess ||
       cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream) != cudaSuccess ||
       cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * kCounters, c->stream) != cudaSuccess)
     return bail(fail(B200LDA_ECUDA, "cudaMemset failed"));
@@ -994,7 +1067,12 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_nwk_b);
   dev_free(c->d_nk);
   dev_free(c->d_nk_delta);
-  dev_free(c->d_exchange);
+  if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
+  if (c->apply_stream) cudaStreamDestroy(c->apply_stream);
+  if (c->ev_applied) cudaEventDestroy(c->ev_applied);
+  for (int i = 0; i < kExchangeSlabs; ++i)
+    if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
   dev_free(c->d_invden);
   dev_free(c->d_ab);
   dev_free(c->d_prior);
@@ -1038,31 +1116,36 @@ int b200lda_load_corpus(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr
   return B200LDA_OK;
 }
 
-int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
+namespace {
+// z32 / z16: the caller's topics in either width (at most one non-null); both null: Philox draw.
+int init_assignments_impl(b200lda_ctx* c, const int32_t* z32, const uint16_t* z16) {
   TRY(enter(c));
   if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
   if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
   c->assigned = false;
   c->hot_count = -1;
+  c->snapshot_valid = false;
   DeviceCorpus& cp = c->corp;
   const int64_t N = cp.N;
+  int bad = 0;
   if (N > 0) {
-    if (z) {
+    CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+    if (z32) {
       TRY(ensure_stage(c, sizeof(int32_t) * (size_t)N));
-      CU(cudaMemcpyAsync(c->d_stage, z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
-      CU(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+      CU(cudaMemcpyAsync(c->d_stage, z32, sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
       k_narrow_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, reinterpret_cast<const int32_t*>(c->d_stage),
                                                           cp.d_z, c->d_bad);
-      int bad = 0;
-      CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      if (bad) return fail(B200LDA_ERANGE, "z holds a topic outside [0, %d)", c->K);
+    } else if (z16) {  // the device's own width: no staging, half the bytes over the bus
+      CU(cudaMemcpyAsync(cp.d_z, z16, sizeof(uint16_t) * N, cudaMemcpyHostToDevice, c->stream));
+      k_validate_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, cp.d_z, c->d_bad);
     } else {
       k_init_z<<<grid_for(c, N, 256), 256, 0, c->stream>>>(N, c->K, c->cfg.seed, c->cfg.global_token_offset, cp.d_z);
     }
+    if (z32 || z16) CU(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->launches += 1;
   }
   // n_wk by integer atomics straight from the doc -> token order, n_k as its column sums
+  // (an out-of-range topic was clamped to 0 above and is reported below: nothing reads out of bounds)
   const size_t VK = (size_t)c->V * c->K;
   CU(cudaMemsetAsync(c->d_nwk, 0, sizeof(int32_t) * VK, c->stream));
   CU(cudaMemsetAsync(c->d_nk, 0, sizeof(int32_t) * c->K, c->stream));
@@ -1076,18 +1159,26 @@ int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) {
   }
   TRY(build_doc_rows(c, cp));
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // the one synchronisation of the call (the caller's z is borrowed)
+  if (bad) return fail(B200LDA_ERANGE, "z holds a topic outside [0, %d)", c->K);
   c->assigned = true;
   return B200LDA_OK;
+}
+}  // namespace
+
+int b200lda_init_assignments(b200lda_ctx* c, const int32_t* z) { return init_assignments_impl(c, z, nullptr); }
+int b200lda_init_assignments_u16(b200lda_ctx* c, const uint16_t* z) {
+  if (!z) return fail(B200LDA_EINVAL, "z is null");
+  return init_assignments_impl(c, nullptr, z);
 }
 
 int b200lda_counts_sync_begin(b200lda_ctx* c) {
   TRY(enter(c));
   TRY(need_ready(c));
-  if (!c->d_exchange) return fail(B200LDA_ESTATE, "count sync needs world_size > 1");
+  if (c->cfg.world_size <= 1) return fail(B200LDA_ESTATE, "count sync needs world_size > 1");
   const size_t VK = (size_t)c->V * c->K;
-  CU(cudaMemcpyAsync(c->d_exchange, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_exchange + VK, c->d_nk, sizeof(int32_t) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  // the exchange buffer is d_nwk itself: this shard's counts, its n_k in the tail
+  CU(cudaMemcpyAsync(c->d_nwk + VK, c->d_nk, sizeof(int32_t) * c->K, cudaMemcpyDeviceToDevice, c->stream));
   c->in_sync = true;
   return B200LDA_OK;
 }
@@ -1096,8 +1187,12 @@ int b200lda_counts_sync_end(b200lda_ctx* c) {
   TRY(enter(c));
   if (!c->in_sync) return fail(B200LDA_ESTATE, "b200lda_counts_sync_end without b200lda_counts_sync_begin");
   const size_t VK = (size_t)c->V * c->K;
-  CU(cudaMemcpyAsync(c->d_nwk, c->d_exchange, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_nk, c->d_exchange + VK, sizeof(int32_t) * c->K, cudaMemcpyDeviceToDevice, c->stream));
+  k_install_nk_tail<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_nwk + VK, c->d_nwk_b + VK);
+  CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
+  c->launches += 1;
+  CU(cudaGetLastError());
+  c->snapshot_valid = true;
+  c->hot_count = -1;
   c->in_sync = false;
   return B200LDA_OK;
 }
@@ -1109,20 +1204,32 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
   const size_t VK = (size_t)c->V * c->K;
   if (!deferred && c->table_refresh != 1) TRY(build_hot_words(c));  // once per corpus
+  if (multi && !c->snapshot_valid) {  // counts were installed without a count sync (restored state, one-shard tests)
+    CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_nwk + VK, 0, sizeof(int32_t) * c->K, c->stream));
+    CU(cudaMemsetAsync(c->d_nwk_b + VK, 0, sizeof(int32_t) * c->K, c->stream));
+    c->snapshot_valid = true;
+  }
   TRY(next_event_quad(c));
   CU(cudaEventRecord(c->ev[0], c->stream));
   TRY(build_tables(c, !deferred));
   CU(cudaEventRecord(c->ev[1], c->stream));
-  if (deferred || multi)
+  if (deferred && !multi)
     CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
-  // DEFERRED: read the frozen d_nwk, write moves into the copy d_nwk_b.
-  // LIVE:     read and write d_nwk in place (d_nwk_b keeps the sweep-start snapshot if multi).
-  SweepParams p = sweep_params(c, c->corp, c->d_nwk, deferred ? c->d_nwk_b : c->d_nwk, (uint32_t)(c->sweeps_done + 1));
+  // one shard: LIVE reads and writes d_nwk; DEFERRED reads the frozen d_nwk, writes the copy d_nwk_b
+  //            (swapped in at the end of the sweep).
+  // shards:    d_nwk_b = the global counts of the sweep start on every shard. LIVE reads and writes
+  //            d_nwk; DEFERRED reads d_nwk_b and writes d_nwk. Either way d_nwk ends the sweep as
+  //            "start + this shard's moves" with the n_k moves in its tail: the exchange buffer.
+  const int32_t* rd = (deferred && multi) ? c->d_nwk_b : c->d_nwk;
+  int32_t* wr = (deferred && !multi) ? c->d_nwk_b : c->d_nwk;
+  SweepParams p = sweep_params(c, c->corp, rd, wr, (uint32_t)(c->sweeps_done + 1));
+  if (multi) p.nk_delta = c->d_nwk + VK;
   if (deferred) {
     TRY((launch_sweep<MODE_UPDATE, false>(c, c->corp, p)));
   } else {
-    // rows the sampling warps rebuild per token (20-bit fixed point): every word's row is rebuilt
-    // table_refresh times per sweep, the first of them by build_tables above
+    // every hot word's prior row is rebuilt table_refresh times per sweep, the first of them by
+    // build_tables above, the others by the refreshers beside the bulk launches
     const int refresh = c->table_refresh > 0 ? c->table_refresh : auto_table_refresh(c, c->corp);
     c->last_refresh = refresh;
     p.prior_sel = c->d_prior_sel;
@@ -1132,40 +1239,21 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   }
   k_accumulate_stats<<<1, 32, 0, c->stream>>>(c->d_counters + 1, c->d_counters + 5);
   CU(cudaEventRecord(c->ev[2], c->stream));
-  if (multi) {
-    const int32_t* after = deferred ? c->d_nwk_b : c->d_nwk;
-    const int32_t* before = deferred ? c->d_nwk : c->d_nwk_b;
-    k_form_delta<<<grid_for(c, (int64_t)(VK / 4 + 1), 256), 256, 0, c->stream>>>(VK, c->K, after, before, c->d_nk_delta,
-                                                                                c->d_exchange);
-    c->launches += 1;
-    CU(cudaGetLastError());
-  }
   c->in_sweep = true;
   return B200LDA_OK;
 }
 
 int b200lda_exchange_buffer(b200lda_ctx* c, void** d_buf, int64_t* count) {
   if (!c || !d_buf || !count) return fail(B200LDA_EINVAL, "null argument");
-  *d_buf = c->d_exchange;
-  *count = c->d_exchange ? (int64_t)((size_t)c->V * c->K + c->K) : 0;
+  const bool multi = c->cfg.world_size > 1;
+  *d_buf = multi ? c->d_nwk : nullptr;
+  *count = multi ? (int64_t)((size_t)c->V * c->K + c->K) : 0;
   return B200LDA_OK;
 }
 
-int b200lda_sweep_end(b200lda_ctx* c) {
-  TRY(enter(c));
-  if (!c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_end without b200lda_sweep_begin");
-  const bool multi = c->cfg.world_size > 1;
-  const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
-  const size_t VK = (size_t)c->V * c->K;
-  if (multi) {
-    const int32_t* before = deferred ? c->d_nwk : c->d_nwk_b;
-    k_apply_delta<<<grid_for(c, (int64_t)(VK / 4 + 1), 256), 256, 0, c->stream>>>(VK, c->K, c->d_nwk, before, c->d_exchange,
-                                                                                 c->d_nk, c->d_nk_delta);
-  } else {
-    if (deferred) std::swap(c->d_nwk, c->d_nwk_b);
-    k_apply_nk<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_nk_delta);
-  }
-  c->launches += 1;
+namespace {
+// bookkeeping shared by every way a sweep ends
+int sweep_close(b200lda_ctx* c) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[3], c->stream));
   c->ev_pending += 1;
@@ -1173,6 +1261,84 @@ int b200lda_sweep_end(b200lda_ctx* c) {
   c->sweeps_done += 1;
   c->tokens_sampled += c->corp.N;
   return B200LDA_OK;
+}
+
+// Slab s of the exchange buffer: [*i0, *i1) cells of the V x K part.
+void exchange_slab(const b200lda_ctx* c, int s, size_t* i0, size_t* i1) {
+  const size_t VK = (size_t)c->V * c->K;
+  const size_t per = ((VK + kExchangeSlabs - 1) / kExchangeSlabs + 3) & ~(size_t)3;
+  *i0 = std::min(VK, per * (size_t)s);
+  *i1 = std::min(VK, per * (size_t)(s + 1));
+}
+
+// The exchange done by the library over NCCL, for `n` contexts driven by this thread (n = 1: one
+// process per GPU). The K-cell tail goes first (n_k), then the V x K cells in slabs: slab s is
+// applied on the context's second stream while NCCL reduces slab s + 1.
+int exchange_nccl(b200lda_ctx** ctxs, int n) {
+  TRY(load_nccl());
+  for (int i = 0; i < n; ++i)
+    if (!ctxs[i]->comm) return fail(B200LDA_ESTATE, "context %d has no communicator (b200lda_comm_init / b200lda_group_comm_init)", i);
+  const size_t VK = (size_t)ctxs[0]->V * ctxs[0]->K;
+  const int K = ctxs[0]->K;
+  const int nm1 = ctxs[0]->cfg.world_size - 1;
+  NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < n; ++i) {
+    b200lda_ctx* c = ctxs[i];
+    NCCL(g_nccl.AllReduce(c->d_nwk + VK, c->d_nwk + VK, (size_t)K, ncclInt32, ncclSum, c->comm, c->stream));
+  }
+  NCCL(g_nccl.GroupEnd());
+  for (int i = 0; i < n; ++i) {
+    b200lda_ctx* c = ctxs[i];
+    CU(cudaSetDevice(c->cfg.device));
+    k_apply_nk_tail<<<(K + 255) / 256, 256, 0, c->stream>>>(K, c->d_nk, c->d_nwk + VK, c->d_nwk_b + VK);
+    c->launches += 1;
+  }
+  for (int s = 0; s < kExchangeSlabs; ++s) {
+    size_t i0 = 0, i1 = 0;
+    exchange_slab(ctxs[0], s, &i0, &i1);
+    if (i1 <= i0) continue;
+    NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+      b200lda_ctx* c = ctxs[i];
+      NCCL(g_nccl.AllReduce(c->d_nwk + i0, c->d_nwk + i0, i1 - i0, ncclInt32, ncclSum, c->comm, c->stream));
+    }
+    NCCL(g_nccl.GroupEnd());
+    for (int i = 0; i < n; ++i) {
+      b200lda_ctx* c = ctxs[i];
+      CU(cudaSetDevice(c->cfg.device));
+      CU(cudaEventRecord(c->ev_slab[s], c->stream));
+      CU(cudaStreamWaitEvent(c->apply_stream, c->ev_slab[s], 0));
+      k_apply_sum<<<grid_for(c, (int64_t)((i1 - i0) / 4 + 1), 256), 256, 0, c->apply_stream>>>(i0, i1, nm1, c->d_nwk, c->d_nwk_b);
+      c->launches += 1;
+      CU(cudaGetLastError());
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    b200lda_ctx* c = ctxs[i];
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventRecord(c->ev_applied, c->apply_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_applied, 0));
+  }
+  return B200LDA_OK;
+}
+}  // namespace
+
+int b200lda_sweep_end(b200lda_ctx* c) {
+  TRY(enter(c));
+  if (!c->in_sweep) return fail(B200LDA_ESTATE, "b200lda_sweep_end without b200lda_sweep_begin");
+  const bool multi = c->cfg.world_size > 1;
+  const bool deferred = c->cfg.mode == B200LDA_MODE_DEFERRED;
+  const size_t VK = (size_t)c->V * c->K;
+  if (multi) {  // the caller has summed the exchange buffer over the shards
+    k_apply_nk_tail<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_nwk + VK, c->d_nwk_b + VK);
+    k_apply_sum<<<grid_for(c, (int64_t)(VK / 4 + 1), 256), 256, 0, c->stream>>>(0, VK, c->cfg.world_size - 1, c->d_nwk, c->d_nwk_b);
+    c->launches += 2;
+  } else {
+    if (deferred) std::swap(c->d_nwk, c->d_nwk_b);
+    k_apply_nk<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, c->d_nk_delta);
+    c->launches += 1;
+  }
+  return sweep_close(c);
 }
 
 int b200lda_synchronize(b200lda_ctx* c) {
@@ -1190,12 +1356,17 @@ int b200lda_get_stream(b200lda_ctx* c, void** stream) {
 int b200lda_sweep(b200lda_ctx* c, int32_t n) {
   TRY(enter(c));
   if (n < 0) return fail(B200LDA_EINVAL, "negative sweep count");
-  if (c->cfg.world_size > 1)
-    return fail(B200LDA_ESTATE, "b200lda_sweep needs world_size == 1; shards use sweep_begin / all-reduce / sweep_end");
+  if (c->cfg.world_size > 1 && !c->comm)
+    return fail(B200LDA_ESTATE, "a shard sweeps through b200lda_comm_init + b200lda_sweep, or sweep_begin / all-reduce / sweep_end");
   TRY(need_ready(c));
   for (int32_t i = 0; i < n; ++i) {
     TRY(b200lda_sweep_begin(c));
-    TRY(b200lda_sweep_end(c));
+    if (c->cfg.world_size > 1) {
+      TRY(exchange_nccl(&c, 1));
+      TRY(sweep_close(c));
+    } else {
+      TRY(b200lda_sweep_end(c));
+    }
   }
   CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
@@ -1333,6 +1504,16 @@ int b200lda_get_assignments(b200lda_ctx* c, int32_t* z) {
   c->launches += 1;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(z, d_wide, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200LDA_OK;
+}
+
+int b200lda_get_assignments_u16(b200lda_ctx* c, uint16_t* z) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!z) return fail(B200LDA_EINVAL, "z is null");
+  if (c->corp.N == 0) return B200LDA_OK;
+  CU(cudaMemcpyAsync(z, c->corp.d_z, sizeof(uint16_t) * c->corp.N, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return B200LDA_OK;
 }
@@ -1689,20 +1870,34 @@ int b200lda_group_allreduce(b200lda_ctx** ctxs, int32_t n, int32_t which) {
   if (which != B200LDA_BUFFER_EXCHANGE && which != B200LDA_BUFFER_HYPER) return fail(B200LDA_EINVAL, "bad buffer kind");
   std::vector<int32_t*> bufs((size_t)n);
   size_t count = 0;
+  bool all_comm = true;
   for (int32_t i = 0; i < n; ++i) {
     b200lda_ctx* c = ctxs[i];
     if (!c) return fail(B200LDA_EINVAL, "null context");
-    int32_t* b = which == B200LDA_BUFFER_EXCHANGE ? c->d_exchange : c->d_hyper;
+    int32_t* b = which == B200LDA_BUFFER_EXCHANGE ? (c->cfg.world_size > 1 ? c->d_nwk : nullptr) : c->d_hyper;
     const size_t cnt = which == B200LDA_BUFFER_EXCHANGE ? (size_t)c->V * c->K + c->K
                                                         : ((size_t)c->K + 1) * (size_t)c->hyper_width;
     if (!b) return fail(B200LDA_ESTATE, "context %d has no such buffer (world_size == 1, or hyper_begin not called)", i);
     if (i > 0 && cnt != count) return fail(B200LDA_EINVAL, "contexts disagree on the buffer size");
     count = cnt;
     bufs[(size_t)i] = b;
-    CU(cudaSetDevice(c->cfg.device));
-    CU(cudaStreamSynchronize(c->stream));
+    all_comm = all_comm && c->comm != nullptr;
   }
-  if (n == 1) return B200LDA_OK;
+  if (n == 1 && !(all_comm && ctxs[0]->cfg.world_size > 1)) return B200LDA_OK;
+  if (all_comm) {  // one NCCL all-reduce per context, grouped, each on its context's stream: not blocking
+    TRY(load_nccl());
+    NCCL(g_nccl.GroupStart());
+    for (int32_t i = 0; i < n; ++i)
+      NCCL(g_nccl.AllReduce(bufs[(size_t)i], bufs[(size_t)i], count, ncclInt32, ncclSum, ctxs[i]->comm, ctxs[i]->stream));
+    NCCL(g_nccl.GroupEnd());
+    return B200LDA_OK;
+  }
+  // No communicators (several contexts on ONE device, which NCCL refuses; tests): gather onto the
+  // first context's device with peer copies, add there, copy the sum back. Blocking.
+  for (int32_t i = 0; i < n; ++i) {
+    CU(cudaSetDevice(ctxs[i]->cfg.device));
+    CU(cudaStreamSynchronize(ctxs[i]->stream));
+  }
   b200lda_ctx* root = ctxs[0];
   CU(cudaSetDevice(root->cfg.device));
   TRY(ensure_stage(root, sizeof(int32_t) * count));
@@ -1716,6 +1911,186 @@ int b200lda_group_allreduce(b200lda_ctx** ctxs, int32_t n, int32_t which) {
   for (int32_t i = 1; i < n; ++i)
     CU(cudaMemcpyPeerAsync(bufs[(size_t)i], ctxs[i]->cfg.device, bufs[0], root->cfg.device, sizeof(int32_t) * count, root->stream));
   CU(cudaStreamSynchronize(root->stream));
+  return B200LDA_OK;
+}
+
+// ---- NCCL inside the library ------------------------------------------------------------------
+
+int b200lda_nccl_unique_id(void* id) {
+  if (!id) return fail(B200LDA_EINVAL, "null argument");
+  TRY(load_nccl());
+  static_assert(sizeof(ncclUniqueId) == B200LDA_NCCL_ID_BYTES, "ncclUniqueId size");
+  NCCL(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId*>(id)));
+  return B200LDA_OK;
+}
+
+int b200lda_comm_init(b200lda_ctx* c, const void* id) {
+  TRY(enter(c));
+  if (!id) return fail(B200LDA_EINVAL, "null argument");
+  if (c->cfg.world_size <= 1) return fail(B200LDA_ESTATE, "a communicator needs world_size > 1");
+  if (c->comm) return fail(B200LDA_ESTATE, "the context already has a communicator");
+  TRY(load_nccl());
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NCCL(g_nccl.CommInitRank(&c->comm, c->cfg.world_size, uid, c->cfg.rank));
+  return B200LDA_OK;
+}
+
+int b200lda_group_comm_init(b200lda_ctx** ctxs, int32_t n) {
+  if (!ctxs || n < 2) return fail(B200LDA_EINVAL, "bad context list");
+  TRY(load_nccl());
+  std::vector<int> devs((size_t)n);
+  for (int32_t i = 0; i < n; ++i) {
+    if (!ctxs[i]) return fail(B200LDA_EINVAL, "null context");
+    if (ctxs[i]->cfg.world_size != n || ctxs[i]->cfg.rank != i)
+      return fail(B200LDA_EINVAL, "context %d must be rank %d of %d", i, i, n);
+    if (ctxs[i]->comm) return fail(B200LDA_ESTATE, "context %d already has a communicator", i);
+    devs[(size_t)i] = ctxs[i]->cfg.device;
+    for (int32_t j = 0; j < i; ++j)
+      if (devs[(size_t)j] == devs[(size_t)i])
+        return fail(B200LDA_EINVAL, "contexts %d and %d share device %d: NCCL needs one GPU per shard", j, i, devs[(size_t)i]);
+  }
+  std::vector<ncclComm_t> comms((size_t)n);
+  NCCL(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+  for (int32_t i = 0; i < n; ++i) ctxs[i]->comm = comms[(size_t)i];
+  return B200LDA_OK;
+}
+
+int b200lda_group_sync_counts(b200lda_ctx** ctxs, int32_t n) {
+  if (!ctxs || n < 1) return fail(B200LDA_EINVAL, "bad context list");
+  if (n == 1 && ctxs[0]->cfg.world_size == 1) return B200LDA_OK;
+  for (int32_t i = 0; i < n; ++i) TRY(b200lda_counts_sync_begin(ctxs[i]));
+  if (ctxs[0]->comm) {
+    const size_t count = (size_t)ctxs[0]->V * ctxs[0]->K + ctxs[0]->K;
+    NCCL(g_nccl.GroupStart());
+    for (int32_t i = 0; i < n; ++i)
+      NCCL(g_nccl.AllReduce(ctxs[i]->d_nwk, ctxs[i]->d_nwk, count, ncclInt32, ncclSum, ctxs[i]->comm, ctxs[i]->stream));
+    NCCL(g_nccl.GroupEnd());
+  } else {
+    TRY(b200lda_group_allreduce(ctxs, n, B200LDA_BUFFER_EXCHANGE));
+  }
+  for (int32_t i = 0; i < n; ++i) TRY(b200lda_counts_sync_end(ctxs[i]));
+  return B200LDA_OK;
+}
+
+int b200lda_group_sweep(b200lda_ctx** ctxs, int32_t n, int32_t sweeps) {
+  if (!ctxs || n < 1 || sweeps < 0) return fail(B200LDA_EINVAL, "bad arguments");
+  for (int32_t i = 0; i < n; ++i)
+    if (!ctxs[i] || ctxs[i]->cfg.world_size != ctxs[0]->cfg.world_size) return fail(B200LDA_EINVAL, "bad context list");
+  const bool multi = ctxs[0]->cfg.world_size > 1;
+  bool all_comm = true;
+  for (int32_t i = 0; i < n; ++i) all_comm = all_comm && ctxs[i]->comm != nullptr;
+  for (int32_t it = 0; it < sweeps; ++it) {
+    for (int32_t i = 0; i < n; ++i) TRY(b200lda_sweep_begin(ctxs[i]));
+    if (multi && all_comm) {
+      TRY(exchange_nccl(ctxs, n));
+      for (int32_t i = 0; i < n; ++i) {
+        CU(cudaSetDevice(ctxs[i]->cfg.device));
+        TRY(sweep_close(ctxs[i]));
+      }
+    } else {
+      if (multi) TRY(b200lda_group_allreduce(ctxs, n, B200LDA_BUFFER_EXCHANGE));
+      for (int32_t i = 0; i < n; ++i) TRY(b200lda_sweep_end(ctxs[i]));
+    }
+  }
+  for (int32_t i = 0; i < n; ++i) TRY(b200lda_synchronize(ctxs[i]));
+  return B200LDA_OK;
+}
+
+// ---- resumable state ----------------------------------------------------------------------------
+
+namespace {
+struct StateHeader {
+  char magic[8];
+  int32_t version, K, V, mode;
+  int64_t D, N, sweeps_done;
+  uint64_t seed, corpus_hash;
+  double beta;
+  int32_t rank, world_size;
+  int64_t global_token_offset;
+};
+constexpr char kStateMagic[8] = {'B', '2', '0', '0', 'L', 'D', 'A', '1'};
+
+int corpus_hash(b200lda_ctx* c, uint64_t* out) {
+  const DeviceCorpus& cp = c->corp;
+  unsigned long long* d_h = c->d_counters + 13;
+  CU(cudaMemsetAsync(d_h, 0, sizeof(unsigned long long), c->stream));
+  if (cp.D > 0) k_hash_i64<<<grid_for(c, cp.D + 1, 256), 256, 0, c->stream>>>(cp.D + 1, cp.d_doc_ptr, d_h);
+  if (cp.N > 0) k_hash_i32<<<grid_for(c, cp.N, 256), 256, 0, c->stream>>>(cp.N, cp.d_tok_word, d_h);
+  c->launches += 2;
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, d_h, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  *out = (uint64_t)h;
+  return B200LDA_OK;
+}
+}  // namespace
+
+int b200lda_state_size(b200lda_ctx* c, int64_t* bytes) {
+  if (!c || !bytes) return fail(B200LDA_EINVAL, "null argument");
+  *bytes = (int64_t)(sizeof(StateHeader) + sizeof(double) * (size_t)c->K + sizeof(uint16_t) * (size_t)c->corp.N);
+  return B200LDA_OK;
+}
+
+int b200lda_get_state(b200lda_ctx* c, void* buf, int64_t bytes) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  int64_t need = 0;
+  TRY(b200lda_state_size(c, &need));
+  if (!buf || bytes < need) return fail(B200LDA_EINVAL, "state buffer too small (%lld bytes needed)", (long long)need);
+  StateHeader h{};
+  memcpy(h.magic, kStateMagic, 8);
+  h.version = 1;
+  h.K = c->K;
+  h.V = c->V;
+  h.mode = c->cfg.mode;
+  h.D = c->corp.D;
+  h.N = c->corp.N;
+  h.sweeps_done = c->sweeps_done;
+  h.seed = c->cfg.seed;
+  h.beta = c->beta;
+  h.rank = c->cfg.rank;
+  h.world_size = c->cfg.world_size;
+  h.global_token_offset = c->cfg.global_token_offset;
+  TRY(corpus_hash(c, &h.corpus_hash));
+  char* out = static_cast<char*>(buf);
+  memcpy(out, &h, sizeof(h));
+  memcpy(out + sizeof(h), c->alpha.data(), sizeof(double) * (size_t)c->K);
+  if (c->corp.N > 0) {
+    CU(cudaMemcpyAsync(out + sizeof(h) + sizeof(double) * (size_t)c->K, c->corp.d_z, sizeof(uint16_t) * c->corp.N,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return B200LDA_OK;
+}
+
+int b200lda_set_state(b200lda_ctx* c, const void* buf, int64_t bytes) {
+  TRY(enter(c));
+  if (!c->corpus_loaded) return fail(B200LDA_ESTATE, "no corpus loaded (call b200lda_load_corpus)");
+  if (c->in_sweep || c->in_sync) return fail(B200LDA_ESTATE, "a sweep or count sync is open");
+  if (!buf || bytes < (int64_t)sizeof(StateHeader)) return fail(B200LDA_EINVAL, "not a state blob");
+  StateHeader h;
+  memcpy(&h, buf, sizeof(h));
+  if (memcmp(h.magic, kStateMagic, 8) != 0 || h.version != 1) return fail(B200LDA_EINVAL, "not a b200lda state blob (magic / version)");
+  if (h.K != c->K || h.V != c->V) return fail(B200LDA_EINVAL, "state is for K=%d V=%d, context has K=%d V=%d", h.K, h.V, c->K, c->V);
+  if (h.D != c->corp.D || h.N != c->corp.N)
+    return fail(B200LDA_EINVAL, "state is for %lld documents / %lld tokens, the loaded corpus has %lld / %lld", (long long)h.D,
+                (long long)h.N, (long long)c->corp.D, (long long)c->corp.N);
+  const int64_t need = (int64_t)(sizeof(StateHeader) + sizeof(double) * (size_t)c->K + sizeof(uint16_t) * (size_t)h.N);
+  if (bytes < need) return fail(B200LDA_EINVAL, "state blob truncated (%lld of %lld bytes)", (long long)bytes, (long long)need);
+  uint64_t hash = 0;
+  TRY(corpus_hash(c, &hash));
+  if (hash != h.corpus_hash) return fail(B200LDA_EINVAL, "state belongs to another corpus (checksum of doc_ptr / tok_word differs)");
+  const char* in = static_cast<const char*>(buf);
+  std::vector<double> alpha((size_t)c->K);
+  memcpy(alpha.data(), in + sizeof(h), sizeof(double) * (size_t)c->K);
+  TRY(b200lda_set_alpha(c, alpha.data()));
+  TRY(b200lda_set_beta(c, h.beta));
+  c->cfg.seed = h.seed;  // the Philox key is part of the chain's identity
+  c->cfg.global_token_offset = h.global_token_offset;
+  TRY(init_assignments_impl(c, nullptr, reinterpret_cast<const uint16_t*>(in + sizeof(h) + sizeof(double) * (size_t)c->K)));
+  c->sweeps_done = h.sweeps_done;
   return B200LDA_OK;
 }
 

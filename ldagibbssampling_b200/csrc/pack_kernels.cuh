@@ -35,6 +35,40 @@ __global__ void k_narrow_z(int64_t N, int K, const int32_t* __restrict__ in, uin
   }
 }
 
+// Order-dependent checksum of an array: sum over i of mix(i, x[i]) (commutative, so a parallel
+// reduction gives one well-defined value). Guards a state blob against the wrong corpus.
+__device__ __forceinline__ unsigned long long hash_mix(unsigned long long i, unsigned long long x) {
+  unsigned long long z = (i + 1ull) * 0x9E3779B97F4A7C15ull ^ (x + 0xD1B54A32D192ED03ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <typename T>
+__device__ __forceinline__ void hash_array(int64_t n, const T* __restrict__ x, unsigned long long* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc += hash_mix((unsigned long long)i, (unsigned long long)(long long)x[i]);
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+__global__ void k_hash_i64(int64_t n, const int64_t* __restrict__ x, unsigned long long* __restrict__ out) { hash_array(n, x, out); }
+__global__ void k_hash_i32(int64_t n, const int32_t* __restrict__ x, unsigned long long* __restrict__ out) { hash_array(n, x, out); }
+
+// Validation of topics handed over in their device width (16 bits): flags any z >= K (and clamps
+// it to 0 so that nothing downstream reads out of bounds before the error is reported).
+__global__ void k_validate_z(int64_t N, int K, uint16_t* __restrict__ z, int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool any = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    if ((int)z[i] >= K) {
+      any = true;
+      z[i] = 0;
+    }
+  }
+  if (any) *bad = 1;
+}
+
 __global__ void k_widen_z(int64_t N, const uint16_t* __restrict__ in, int32_t* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) out[i] = (int32_t)in[i];

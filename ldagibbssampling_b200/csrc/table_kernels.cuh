@@ -138,44 +138,48 @@ __global__ void k_apply_nk(int K, int32_t* __restrict__ nk, int32_t* __restrict_
   nk_delta[k] = 0;
 }
 
-// exchange[i] = after[i] - before[i]  (i < VK),  exchange[VK + k] = nk_delta[k]
-__global__ void k_form_delta(size_t VK, int K, const int32_t* __restrict__ after,
-                             const int32_t* __restrict__ before, const int32_t* __restrict__ nk_delta,
-                             int32_t* __restrict__ exchange) {
+// AD-LDA exchange, in place. Every shard starts a sweep with the same global counts G (kept in
+// `snap`), samples, and holds A_r = G + (its own moves) in `sum` (plus its n_k moves in the K-cell
+// tail behind the V x K cells). The caller all-reduces `sum` (tail included) over the N shards:
+// sum = sum_r A_r. The new global counts are  sum - (N - 1) G ; they go to BOTH buffers (the next
+// sweep's live / written copy and its snapshot). Replaces Mallet's sumTypeTopicCounts + copy-back
+// (setNumThreads(n), reference cmu_ron/TrainAndPredict.java:164) without a delta buffer:
+// two reads and two writes per cell around one collective. [i0, i1) = the slab of cells to apply
+// (the library pipelines slabs behind the all-reduce of the next one).
+__global__ void k_apply_sum(size_t i0, size_t i1, int nm1, int32_t* __restrict__ sum, int32_t* __restrict__ snap) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t n4 = VK >> 2;
-  const int4* a4 = reinterpret_cast<const int4*>(after);
-  const int4* b4 = reinterpret_cast<const int4*>(before);
-  int4* e4 = reinterpret_cast<int4*>(exchange);
-  for (size_t i = tid; i < n4; i += stride) {
-    const int4 a = a4[i], b = b4[i];
-    e4[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+  const size_t a0 = (i0 + 3) & ~(size_t)3, a1 = i1 & ~(size_t)3;  // int4 body, scalar edges
+  if (a0 < a1) {
+    int4* s4 = reinterpret_cast<int4*>(sum);
+    int4* g4 = reinterpret_cast<int4*>(snap);
+    for (size_t i = (a0 >> 2) + tid; i < (a1 >> 2); i += stride) {
+      const int4 s = s4[i], g = g4[i];
+      const int4 n = make_int4(s.x - nm1 * g.x, s.y - nm1 * g.y, s.z - nm1 * g.z, s.w - nm1 * g.w);
+      s4[i] = n;
+      g4[i] = n;
+    }
+    for (size_t i = i0 + tid; i < a0; i += stride) sum[i] = snap[i] = sum[i] - nm1 * snap[i];
+    for (size_t i = a1 + tid; i < i1; i += stride) sum[i] = snap[i] = sum[i] - nm1 * snap[i];
+  } else {
+    for (size_t i = i0 + tid; i < i1; i += stride) sum[i] = snap[i] = sum[i] - nm1 * snap[i];
   }
-  for (size_t i = (n4 << 2) + tid; i < VK; i += stride) exchange[i] = after[i] - before[i];
-  for (size_t k = tid; k < (size_t)K; k += stride) exchange[VK + k] = nk_delta[k];
 }
-
-// nwk[i] = before[i] + exchange[i];  nk[k] += exchange[VK + k];  nk_delta = 0
-// nwk and before may be the SAME buffer (DEFERRED mode applies the sum in place): no __restrict__ on them.
-__global__ void k_apply_delta(size_t VK, int K, int32_t* nwk, const int32_t* before,
-                              const int32_t* __restrict__ exchange, int32_t* __restrict__ nk,
-                              int32_t* __restrict__ nk_delta) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t n4 = VK >> 2;
-  const int4* b4 = reinterpret_cast<const int4*>(before);
-  const int4* e4 = reinterpret_cast<const int4*>(exchange);
-  int4* o4 = reinterpret_cast<int4*>(nwk);
-  for (size_t i = tid; i < n4; i += stride) {
-    const int4 b = b4[i], e = e4[i];
-    o4[i] = make_int4(b.x + e.x, b.y + e.y, b.z + e.z, b.w + e.w);
-  }
-  for (size_t i = (n4 << 2) + tid; i < VK; i += stride) nwk[i] = before[i] + exchange[i];
-  for (size_t k = tid; k < (size_t)K; k += stride) {
-    nk[k] += exchange[VK + k];
-    nk_delta[k] = 0;
-  }
+// nk[k] += tail[k] (the summed n_k moves); both buffers' tails are cleared for the next sweep.
+__global__ void k_apply_nk_tail(int K, int32_t* __restrict__ nk, int32_t* __restrict__ tail_sum, int32_t* __restrict__ tail_snap) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  nk[k] += tail_sum[k];
+  tail_sum[k] = 0;
+  tail_snap[k] = 0;
+}
+// start-up: nk[k] = tail[k] (the summed per-shard n_k), tails cleared
+__global__ void k_install_nk_tail(int K, int32_t* __restrict__ nk, int32_t* __restrict__ tail_sum, int32_t* __restrict__ tail_snap) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  nk[k] = tail_sum[k];
+  tail_sum[k] = 0;
+  tail_snap[k] = 0;
 }
 
 }  // namespace b200lda

@@ -13,6 +13,9 @@ same with `ParallelTopicModel` imported from here:
 
 All arithmetic happens in libb200lda.so on the GPU; there is no CPU fallback. setNumThreads(n)
 means n AD-LDA shards = n GPUs (one context each; under torch.distributed one rank = one shard).
+The per-sweep count exchange is the library's own (NCCL loaded by libb200lda.so): one communicator
+set for the contexts of this process (b200lda_group_comm_init) or, one process per GPU, a
+communicator per rank from a unique id broadcast through torch.distributed (b200lda_comm_init).
 """
 from __future__ import annotations
 
@@ -26,38 +29,11 @@ from .instances import Alphabet, FeatureSequence, Instance, InstanceList, LabelS
 from .partition import partition_by_tokens, shard_corpus
 
 
-class _LocalReducer:
-    """Sums the shards' exchange buffers when every shard lives in this process (several contexts,
-    one per GPU or several per GPU): the library's own in-process all-reduce
-    (b200lda_group_allreduce: peer copies + a device add), no host round trip and no NCCL."""
-
-    def __init__(self, samplers, which="exchange"):
-        self.which = 0 if which == "exchange" else 1
-
-    def __call__(self, samplers):
-        _capi.group_allreduce(samplers, self.which)
-
-
 class _DevBuf:
+    """A device buffer of the library as something torch.as_tensor accepts (tests, tools)."""
+
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
-
-
-class _DistReducer:
-    """One process per GPU: the exchange is a torch.distributed all-reduce (NCCL over NVLink)
-    enqueued on the sampler's stream between sweep_begin and sweep_end."""
-
-    def __init__(self, sampler, group=None, which="exchange"):
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist, self.group = torch, dist, group
-        ptr, n = sampler.exchange_buffer() if which == "exchange" else sampler.hyper_buffer()
-        self.buf = torch.as_tensor(_DevBuf(ptr, n), device=torch.device("cuda", sampler.device))
-        self.stream = torch.cuda.ExternalStream(sampler.stream(), device=torch.device("cuda", sampler.device))
-
-    def __call__(self, samplers):
-        with self.torch.cuda.stream(self.stream):
-            self.dist.all_reduce(self.buf, op=self.dist.ReduceOp.SUM, group=self.group)
 
 
 class ParallelTopicModel:
@@ -210,6 +186,12 @@ class ParallelTopicModel:
                               global_token_offset=sh.token_begin, global_doc_offset=sh.doc_begin)
             s.set_alpha(self.alpha)
             s.load_corpus(dp, tok)
+            restore = getattr(self, "_restore", None)
+            if restore is not None and len(restore) == world:
+                s.set_state(restore[r])      # alpha, beta, seed, sweep counter, z: the chain continues
+                self._samplers.append(s)
+                self._shards.append(sh)
+                continue
             if self._z_host is None or self._new_from == 0:
                 s.init_assignments(None)
             else:
@@ -222,30 +204,27 @@ class ParallelTopicModel:
             s.set_sweep_counter(self._iterationsSoFar)
             self._samplers.append(s)
             self._shards.append(sh)
-        self._reducer = None
         if world > 1:
-            self._sync_global_counts()
+            self._init_communicators(my_rank)
+            _capi.group_sync_counts(self._samplers)   # Mallet's sumTypeTopicCounts at start-up
+            for s in self._samplers:
+                s.synchronize()
         self._dirty = False
         self._z_host = None
+        self._restore = None
         self._push_assignments_to_data()
 
-    def _sync_global_counts(self):
-        """Each shard built n_wk / n_k from its own documents; one all-reduce of the counts makes
-        every replica global (Mallet's sumTypeTopicCounts at start-up)."""
-        for s in self._samplers:
-            s.counts_sync_begin()
-        self._get_reducer()(self._samplers)
-        for s in self._samplers:
-            s.counts_sync_end()
-        for s in self._samplers:
-            s.synchronize()
-
-    def _get_reducer(self):
-        if self._reducer is None:
-            _, my_rank = self._world()
-            self._reducer = (_DistReducer(self._samplers[0], self.process_group) if my_rank is not None
-                             else _LocalReducer(self._samplers))
-        return self._reducer
+    def _init_communicators(self, my_rank):
+        """NCCL communicators inside the library. One process per GPU: rank 0's unique id travels
+        through torch.distributed. All shards in this process: one communicator set, when every
+        shard has its own GPU (several contexts on one GPU - tests - fall back to peer copies)."""
+        if my_rank is not None:
+            import torch.distributed as dist
+            box = [_capi.nccl_unique_id() if my_rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=self.process_group)
+            self._samplers[0].comm_init(box[0])
+        elif len({s.device for s in self._samplers}) == len(self._samplers):
+            _capi.group_comm_init(self._samplers)
 
     # -- estimate ---------------------------------------------------------------------------------
     def estimate(self):
@@ -259,38 +238,35 @@ class ParallelTopicModel:
         n = self.numIterations
         world, my_rank = self._world()
         optimizing = self.optimizeInterval != 0 and n > self.burninPeriod
-        if world == 1 and not optimizing:
-            self._samplers[0].sweep(n)
+        if not optimizing:
+            _capi.group_sweep(self._samplers, n)
         else:
-            reducer = self._get_reducer() if world > 1 else None
-            hyper_reducer = None
-            if optimizing:
-                width = int(np.diff(self._doc_ptr).max()) + 1 if len(self._doc_ptr) > 1 else 1
-                for s in self._samplers:
-                    s.hyper_begin(width)
-                if world > 1:
-                    hyper_reducer = (_DistReducer(self._samplers[0], self.process_group, which="hyper")
-                                     if my_rank is not None else _LocalReducer(self._samplers, which="hyper"))
+            width = int(np.diff(self._doc_ptr).max()) + 1 if len(self._doc_ptr) > 1 else 1
+            for s in self._samplers:
+                s.hyper_begin(width)
             # Mallet's estimate(): iteration counts from 1 on every call; statistics are collected on
             # iterations > burninPeriod that are multiples of saveSampleInterval, alpha and beta are
             # re-estimated on those that are multiples of optimizeInterval.
-            for iteration in range(1, n + 1):
-                if world == 1:
-                    self._samplers[0].sweep(1)
+            iteration = 0
+            while iteration < n:
+                # sweeps up to the next iteration that collects or optimises go down in one call
+                nxt = n
+                if iteration + 1 > self.burninPeriod:
+                    nxt = iteration + 1
+                    while nxt < n and nxt % self.saveSampleInterval and nxt % self.optimizeInterval:
+                        nxt += 1
                 else:
-                    for s in self._samplers:
-                        s.sweep_begin()
-                    reducer(self._samplers)
-                    for s in self._samplers:
-                        s.sweep_end()
-                if not optimizing or iteration <= self.burninPeriod:
+                    nxt = min(n, self.burninPeriod)
+                _capi.group_sweep(self._samplers, nxt - iteration)
+                iteration = nxt
+                if iteration <= self.burninPeriod:
                     continue
                 if iteration % self.saveSampleInterval == 0:
                     for s in self._samplers:
                         s.hyper_collect()
                 if iteration % self.optimizeInterval == 0:
-                    if hyper_reducer is not None:
-                        hyper_reducer(self._samplers)
+                    if world > 1:
+                        _capi.group_allreduce(self._samplers, 1)
                     for s in self._samplers:
                         s.optimize_alpha()
                         s.optimize_beta()
@@ -398,6 +374,53 @@ class ParallelTopicModel:
                     out.write(f" {int(k)} {repr(float(theta[k]))}")
                 out.write(" \n")
 
+    # -- checkpoint (Mallet: the model is Serializable; the reference writes it with
+    #    ObjectOutputStream and skips training when the file exists, cmu_ron/TrainAndPredict.java:179-226)
+    def write(self, file):
+        """The whole model as one .npz: corpus, alphabet, configuration and, per shard, the
+        library's state blob (alpha, beta, Philox seed, sweep counter, z). read() continues the
+        chain where it stopped - bit-identically in DEFERRED mode."""
+        import json
+        if self._dirty:
+            self._pull_assignments()
+            self._build_device_state()
+        meta = {k: getattr(self, k) for k in ("numTopics", "alphaSum", "beta", "numIterations", "burninPeriod",
+                                              "optimizeInterval", "saveSampleInterval", "showTopicsInterval",
+                                              "wordsPerTopic", "numThreads", "randomSeed", "mode", "_iterationsSoFar")}
+        meta["names"] = [ta.instance.getName() for ta in self.data]
+        meta["sources"] = [ta.instance.getSource() for ta in self.data]
+        meta["alphabet"] = [str(x) for x in self.alphabet.toArray()]
+        blobs = {f"state_{i}": np.frombuffer(s.get_state(), np.uint8) for i, s in enumerate(self._samplers)}
+        with (open(file, "wb") if not hasattr(file, "write") else _nullctx(file)) as out:
+            np.savez(out, meta=np.frombuffer(json.dumps(meta).encode(), np.uint8), doc_ptr=self._doc_ptr, tok=self._tok,
+                     alpha=self.alpha, **blobs)
+
+    @classmethod
+    def read(cls, file, devices=None) -> "ParallelTopicModel":
+        import json
+        with np.load(file) as f:
+            meta = json.loads(f["meta"].tobytes().decode())
+            doc_ptr, tok, alpha = f["doc_ptr"], f["tok"], f["alpha"]
+            blobs = [f[k].tobytes() for k in sorted((k for k in f.files if k.startswith("state_")), key=lambda k: int(k[6:]))]
+        m = cls(meta["numTopics"], meta["alphaSum"], meta["beta"])
+        for k in ("numIterations", "burninPeriod", "optimizeInterval", "saveSampleInterval", "showTopicsInterval",
+                  "wordsPerTopic", "numThreads", "randomSeed", "mode", "_iterationsSoFar"):
+            setattr(m, k, meta[k])
+        m.alpha = np.asarray(alpha, np.float64)
+        m.devices = devices
+        m.alphabet = Alphabet(meta["alphabet"])
+        il = InstanceList.from_arrays(doc_ptr, tok, m.alphabet, names=meta["names"])
+        for inst, src in zip(il, meta["sources"]):
+            inst._source = src
+            m.data.append(TopicAssignment(inst, LabelSequence(np.zeros(inst.getData().getLength(), np.int32))))
+        m._doc_ptr, m._tok = np.asarray(doc_ptr, np.int64), np.asarray(tok, np.int32)
+        m.numTypes = m.alphabet.size()
+        m.betaSum = m.beta * m.numTypes
+        m._new_from = 0
+        m._restore = blobs
+        m._build_device_state()
+        return m
+
     def close(self):
         for s in self._samplers:
             s.close()
@@ -452,6 +475,11 @@ def _all_gather_ragged(local: np.ndarray, device: int, group) -> np.ndarray:
     parts = [torch.empty(pad, dtype=torch.int32, device=dev) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return np.concatenate([p[:n].cpu().numpy() for p, n in zip(parts, sizes)])
+
+
+def _nullctx(f):
+    import contextlib
+    return contextlib.nullcontext(f)
 
 
 def _fmt(x: float) -> str:

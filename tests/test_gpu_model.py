@@ -356,3 +356,183 @@ def test_large_shape_invariants(oracle):
     st = s.stats()
     assert st["tokens_sampled"] == 6 * N and st["long_docs"] >= 0 and st["mean_doc_topics"] > 1
     s.close()
+
+
+def test_reference_call_order_set_num_threads_after_add_instances(oracle):
+    """The reference configures the model AFTER addInstances (cmu_ron/TrainAndPredict.java:162-166:
+    addInstances, setOptimizeInterval, setNumThreads(4), setNumIterations, estimate): the shards
+    are rebuilt at estimate() and the DEFERRED chain is the single-shard one."""
+    from ldagibbssampling_b200.instances import InstanceList
+    from ldagibbssampling_b200.topic_model import ParallelTopicModel
+    D, V, K = 300, 200, 12
+    dp, tok = oracle.gen_corpus(D, V, 35.0, 6, 41)
+    il = InstanceList.from_arrays(dp, tok)
+    for w in range(il.getDataAlphabet().size(), V):
+        il.getDataAlphabet().lookupIndex(w)
+    model = ParallelTopicModel(K, ALPHA * K, BETA)
+    model.setRandomSeed(9)
+    model.setSamplingMode("deferred")
+    model.addInstances(il)
+    model.setOptimizeInterval(0)
+    model.setNumThreads(2)
+    model.setDevices([0, 0])
+    model.setNumIterations(3)
+    model.estimate()
+    z = np.concatenate([ta.topicSequence.getFeatures() for ta in model.data])
+    want = oracle.spec_sweeps(dp, tok, oracle.init_z(len(tok), K, 9), V, K, ALPHA, BETA, 9, 1, 3)
+    assert np.array_equal(z, want)
+    model.close()
+
+
+@pytest.mark.parametrize("mode_name", ["DEFERRED", "LIVE"])
+def test_state_blob_resumes_the_chain(oracle, mode_name):
+    """Checkpoint / resume (reference save / load / skip-training-if-the-file-exists,
+    cmu_ron/TrainAndPredict.java:179-200, 215-226): 6 sweeps in one go = 3 sweeps, get_state,
+    destroy, a new context on the same corpus, set_state, 3 sweeps - same z, same LL (DEFERRED;
+    LIVE is racy across documents, there the restored counts and the hyper-parameters are checked).
+    Also: uint16 topics in and out, and a blob is refused by the wrong corpus."""
+    L = _L()
+    D, V, K = 500, 300, 24
+    dp, tok = oracle.gen_corpus(D, V, 50.0, 8, 42)
+    mode = getattr(L, "MODE_" + mode_name)
+    a = L.Sampler(K, V, ALPHA * K, BETA, seed=13, mode=mode)
+    a.load_corpus(dp, tok)
+    a.init_assignments(None)
+    a.sweep(6)
+    z6, ll6 = a.assignments(), a.loglik()
+    a.close()
+    b = L.Sampler(K, V, ALPHA * K, BETA, seed=13, mode=mode)
+    b.load_corpus(dp, tok)
+    b.init_assignments(None)
+    b.set_alpha(np.linspace(0.05, 0.2, K))
+    b.set_beta(0.02)
+    b.sweep(3)
+    z3 = b.assignments()
+    assert np.array_equal(b.assignments(np.uint16), z3.astype(np.uint16))
+    blob = b.get_state()
+    b.sweep(3)
+    z_cont, ll_cont = b.assignments(), b.loglik()
+    b.close()
+    c = L.Sampler(K, V, ALPHA * K, BETA, seed=999, mode=mode)   # the blob carries the Philox seed
+    c.load_corpus(dp, tok)
+    c.set_state(blob)
+    assert np.array_equal(c.assignments(), z3)
+    assert np.allclose(c.alpha(), np.linspace(0.05, 0.2, K)) and c.beta() == 0.02
+    assert c.stats()["sweeps_done"] == 3
+    nwk, nk = oracle.count(dp, tok, z3, V, K)
+    assert np.array_equal(c.nwk(), nwk) and np.array_equal(c.nk(), nk)
+    c.sweep(3)
+    if mode_name == "DEFERRED":
+        assert np.array_equal(c.assignments(), z_cont)
+        assert c.loglik() == ll_cont
+    c.close()
+    # without the hyper-parameter change the resumed DEFERRED chain is the uninterrupted one
+    if mode_name == "DEFERRED":
+        d = L.Sampler(K, V, ALPHA * K, BETA, seed=13, mode=mode)
+        d.load_corpus(dp, tok)
+        d.init_assignments(None)
+        d.sweep(3)
+        blob = d.get_state()
+        d.close()
+        e = L.Sampler(K, V, ALPHA * K, BETA, seed=13, mode=mode)
+        e.load_corpus(dp, tok)
+        e.set_state(blob)
+        e.sweep(3)
+        assert np.array_equal(e.assignments(), z6) and e.loglik() == ll6
+        # uint16 topics in
+        e.init_assignments(z6.astype(np.uint16))
+        assert np.array_equal(e.assignments(), z6)
+        with pytest.raises(L.B200LDAError):
+            e.init_assignments(np.full(len(tok), K, np.uint16))
+        e.close()
+    other = L.Sampler(K, V, ALPHA * K, BETA, seed=13, mode=mode)
+    tok2 = tok.copy()
+    tok2[0] = (tok2[0] + 1) % V
+    other.load_corpus(dp, tok2)
+    with pytest.raises(L.B200LDAError):
+        other.set_state(blob)
+    other.close()
+
+
+def test_mirror_write_read_and_update_model_continue_the_chain(oracle, tmp_path):
+    """model.write(file) / ParallelTopicModel.read(file) and the reference's updateModel
+    (addInstances with more documents, then estimate, cmu_ron/TrainAndPredict.java:173-177)."""
+    from ldagibbssampling_b200.instances import InstanceList
+    from ldagibbssampling_b200.topic_model import ParallelTopicModel
+    D, V, K = 300, 200, 10
+    dp, tok = oracle.gen_corpus(D, V, 30.0, 6, 43)
+    il = InstanceList.from_arrays(dp, tok)
+    for w in range(il.getDataAlphabet().size(), V):
+        il.getDataAlphabet().lookupIndex(w)
+
+    def fresh():
+        m = ParallelTopicModel(K, ALPHA * K, BETA)
+        m.setRandomSeed(21)
+        m.setSamplingMode("deferred")
+        m.setOptimizeInterval(0)
+        m.addInstances(il)
+        return m
+
+    a = fresh()
+    a.setNumIterations(6)
+    a.estimate()
+    z6 = np.concatenate([ta.topicSequence.getFeatures() for ta in a.data])
+    a.close()
+    b = fresh()
+    b.setNumIterations(3)
+    b.estimate()
+    path = tmp_path / "model.npz"
+    b.write(str(path))
+    b.close()
+    c = ParallelTopicModel.read(str(path))
+    assert c.getAlphabet().size() == V and len(c.data) == D
+    c.setNumIterations(3)
+    c.estimate()
+    assert np.array_equal(np.concatenate([ta.topicSequence.getFeatures() for ta in c.data]), z6)
+    # updateModel: new documents join, the old documents keep their topics until they are resampled
+    dp2, tok2 = oracle.gen_corpus(40, V, 30.0, 6, 44)
+    il2 = InstanceList.from_arrays(dp2, tok2, c.getAlphabet())
+    c.addInstances(il2)
+    z_after = np.concatenate([ta.topicSequence.getFeatures() for ta in c.data])
+    assert np.array_equal(z_after[:len(tok)], z6) and len(z_after) == len(tok) + len(tok2)
+    c.setNumIterations(2)
+    c.estimate()
+    nwk, nk = c.getTypeTopicCounts()
+    z = np.concatenate([ta.topicSequence.getFeatures() for ta in c.data])
+    want_nwk, want_nk = oracle.count(np.concatenate([dp, dp2[1:] + dp[-1]]), np.concatenate([tok, tok2]), z, V, K)
+    assert np.array_equal(nwk, want_nwk) and np.array_equal(nk, want_nk)
+    c.close()
+
+
+def test_library_nccl_exchange_equals_the_oracle_on_two_gpus(oracle):
+    """The exchange done by the library itself (communicators from b200lda_group_comm_init, grouped
+    slab all-reduces, in-place apply) on two real GPUs: the DEFERRED chain equals the single-shard
+    oracle chain bit for bit and every replica holds the recount. Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = _L()
+    from ldagibbssampling_b200 import _capi
+    from ldagibbssampling_b200.partition import partition_by_tokens, shard_corpus
+    D, V, K = 900, 500, 48
+    dp, tok = oracle.gen_corpus(D, V, 60.0, 10, 45)
+    for mode in (L.MODE_DEFERRED, L.MODE_LIVE):
+        samplers = []
+        for sh in partition_by_tokens(dp, 2):
+            ldp, ltok = shard_corpus(dp, tok, sh)
+            s = L.Sampler(K, V, ALPHA * K, BETA, seed=5, mode=mode, device=sh.rank, rank=sh.rank, world_size=2,
+                          global_token_offset=sh.token_begin, global_doc_offset=sh.doc_begin)
+            s.load_corpus(ldp, ltok)
+            s.init_assignments(None)
+            samplers.append(s)
+        _capi.group_comm_init(samplers)
+        _capi.group_sync_counts(samplers)
+        _capi.group_sweep(samplers, 4)
+        z = np.concatenate([s.assignments() for s in samplers])
+        nwk, nk = oracle.count(dp, tok, z, V, K)
+        for s in samplers:
+            assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+        if mode == L.MODE_DEFERRED:
+            assert np.array_equal(z, oracle.spec_sweeps(dp, tok, oracle.init_z(len(tok), K, 5), V, K, ALPHA, BETA, 5, 1, 4))
+        for s in samplers:
+            s.close()

@@ -28,7 +28,7 @@ def test_library_exports_every_symbol_the_header_declares():
         assert hasattr(lib, name), f"libb200lda.so does not export {name}"
     bound = sorted(n for n, _, _ in _capi.SYMBOLS)
     assert bound == declared, "ctypes binding and include/b200lda.h disagree"
-    assert lib.b200lda_abi_version() == 1
+    assert lib.b200lda_abi_version() == 2
     assert lib.b200lda_last_error() is not None
 
 
