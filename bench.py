@@ -7,7 +7,8 @@
   python bench.py --impl reference ...      # the CPU arm (Mallet-faithful oracle port)
 
 A "step" is one Gibbs sweep over the whole corpus: per-sweep table build + the sampling kernel +
-the AD-LDA count exchange (NCCL all-reduce of the int32 n_wk/n_k delta when N > 1). Default
+the AD-LDA count exchange (the library's own in-place NCCL all-reduce of the n_wk replica when
+N > 1: b200lda_comm_init + b200lda_group_sweep). Default
 workload = BASELINE.json config "synthetic PubMed-shaped corpus: 8.2M docs, V=141k, 738M tokens,
 K=1000" (C4), split over the N GPUs by tokens (strong scaling, as that config states).
 Prints ONE JSON line on rank 0.
@@ -45,7 +46,9 @@ def parse_args():
     ap.add_argument("--topics", type=int, default=0, help="override K (C5 sweep)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-docs", type=int, default=20000, help="documents in the CPU baseline sample")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed CPU work per thread count")
+    ap.add_argument("--after-sweeps", type=int, default=50,
+                    help="second timed block of --steps sweeps starting at this sweep of the chain (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
@@ -53,16 +56,18 @@ def parse_args():
 
 def measured_traffic(workload, K, default_K):
     """DRAM bytes per token of the sampling kernel from the committed ncu capture of this workload
-    (profiles/r01_traffic_<workload>.json: dram__bytes_read.sum + dram__bytes_write.sum over one
+    (profiles/r02_traffic_<workload>.json: dram__bytes_read.sum + dram__bytes_write.sum over one
     sweep's class launches). None when no capture exists for this exact workload / K."""
     if K != default_K:
         return None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", f"r01_traffic_{workload}.json")) as f:
-            d = json.load(f)
-        return float(d["traffic_bytes_per_token"]), d["source"]
-    except Exception:
-        return None, None
+    for rnd in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic_{workload}.json")) as f:
+                d = json.load(f)
+            return float(d["traffic_bytes_per_token"]), d["source"]
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -142,39 +147,67 @@ def host_cpu_model():
     return "unknown CPU"
 
 
+def mallet_probe():
+    """BASELINE.md promises a CPU-Mallet row if a JVM and the pinned jar (reference pom.xml:107-111:
+    cc.mallet:mallet:2.0.7) are found on the box: this is the probe. Neither exists in this image."""
+    import shutil
+    jar = os.path.join(ROOT, "baseline", "_ref", "mallet-2.0.7.jar")
+    return {"java": shutil.which("java") is not None, "mallet_jar": os.path.exists(jar)}
+
+
+def _time_port(dp, tok, V, K, threads, warmup, steps, seconds, z0):
+    """One estimate() call per timed block, as the reference does (the worker replicas are built
+    once per call): returns tokens/s, ms per sweep, the sampling / merge / set-up split, LL/token."""
+    from oracle import oracle as O
+    m = O.MalletModel(K, ALPHA_K * K, BETA, seed=1, threads=threads)
+    m.add_instances(dp, tok, V, z_init=z0)
+    n = len(tok)
+    if warmup:
+        m.estimate(warmup)
+    if steps is None:  # size the block from one probe sweep
+        t0 = time.perf_counter()
+        m.estimate(1)
+        probe = time.perf_counter() - t0
+        steps = int(max(2, min(200, seconds / max(probe, 1e-3))))
+        warmup += 1
+    s0 = m.timers()
+    t0 = time.perf_counter()
+    m.estimate(steps)
+    total = time.perf_counter() - t0
+    s1 = m.timers()
+    setup, sample, merge = (b - a for a, b in zip(s0, s1))
+    ll = m.model_log_likelihood() / n
+    m.close()
+    return {"threads": threads, "tokens_per_s": n * steps / total, "ms_per_sweep": 1e3 * total / steps, "sweeps": steps,
+            "warmup": warmup, "sample_frac": sample / total, "merge_frac": merge / total, "setup_frac": setup / total,
+            "ll_per_token": ll, "ll_after_sweeps": warmup + steps}
+
+
 def run_cpu(workload, K, cpu_docs, warmup, steps=None, seconds=None):
-    """Times AD-LDA sweeps of oracle/mallet_sparse_lda.c with T = all host threads on a bounded
-    sample (cpu_docs documents of the workload's shape). Returns (tokens/s, ms_per_step, info)."""
+    """Times oracle/mallet_sparse_lda.c on a bounded sample (cpu_docs documents of the workload's
+    shape) with 1 thread and with all host threads (Mallet's AD-LDA replicas), from the same initial
+    topics. Returns (tokens/s of the faster one, its ms per sweep, info)."""
     import bench_corpus as BC
     from oracle import oracle as O
     O.build()
     threads = os.cpu_count() or 1
     dp, tok, V, K0 = BC.cpu_sample(workload, cpu_docs)
     K = K or K0
-    m = O.MalletModel(K, ALPHA_K * K, BETA, seed=1, threads=threads)
-    m.add_instances(dp, tok, V)
+    z0 = O.init_z(len(tok), K, 7)
+    runs = [_time_port(dp, tok, V, K, 1, warmup, steps, seconds, z0)]
+    if threads > 1:
+        runs.append(_time_port(dp, tok, V, K, threads, warmup, steps, seconds, z0))
+    best = max(runs, key=lambda r: r["tokens_per_s"])
     n = len(tok)
-    for _ in range(warmup):
-        m.estimate(1)
-    times = []
-    t_begin = time.perf_counter()
-    while True:
-        t0 = time.perf_counter()
-        m.estimate(1)
-        times.append(time.perf_counter() - t0)
-        if steps is not None and len(times) >= steps:
-            break
-        if steps is None and len(times) >= 2 and time.perf_counter() - t_begin >= seconds:
-            break
-    ll = m.model_log_likelihood() / n
-    m.close()
-    total = sum(times)
-    info = {"cores": threads, "kind": "port",
-            "sample": f"{cpu_docs} docs / {n} tokens of the {workload} shape (V={V}, K={K}), "
-                      f"{warmup} warm-up + {len(times)} timed AD-LDA sweeps, T={threads} worker replicas "
-                      f"on {threads} x {host_cpu_model()}",
-            "ll_per_token": ll}
-    return n * len(times) / total, 1e3 * total / len(times), info
+    info = {"cores": best["threads"], "kind": "port",
+            "sample": f"{cpu_docs} docs / {n} tokens of the {workload} shape (V={V}, K={K}) on {threads} x {host_cpu_model()}; "
+                      + "; ".join(f"T={r['threads']}: {r['tokens_per_s']:.3g} tok/s, {r['warmup']} warm-up + {r['sweeps']} timed sweeps "
+                                  f"in one estimate() call, sampling {100 * r['sample_frac']:.0f} % / merge {100 * r['merge_frac']:.0f} % "
+                                  f"/ replica set-up {100 * r['setup_frac']:.0f} % of the time" for r in runs)
+                      + f"; value = the faster (T={best['threads']})",
+            "runs": runs, "ll_per_token": best["ll_per_token"], **mallet_probe(),
+            "corpus": (dp, tok, V, K, z0)}
+    return best["tokens_per_s"], best["ms_per_sweep"], info
 
 
 def reference_arm(args):
@@ -193,7 +226,8 @@ def reference_arm(args):
         "config": {"workload": f"{args.workload}: {w['desc']}", "K": K, "alpha_k": ALPHA_K, "beta": BETA,
                    "note": "reference arm = CPU port of Mallet 2.0.7 SparseLDA/AD-LDA (oracle/), the "
                            "reference itself is Java + an un-vendored jar and no JVM exists here"},
-        "cpu_baseline": {"value": value, "unit": "tokens/s", **{k: info[k] for k in ("cores", "kind", "sample")}},
+        "cpu_baseline": {"value": value, "unit": "tokens/s",
+                         **{k: info[k] for k in ("cores", "kind", "sample", "runs", "java", "mallet_jar")}},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "ll_per_token": info["ll_per_token"],
     }
@@ -248,7 +282,7 @@ def b200_arm(args):
     h_doc_ptr = torch.from_numpy(doc_ptr_g[shard.doc_begin:shard.doc_end + 1] - doc_ptr_g[shard.doc_begin]).pin_memory()
     h_words = torch.empty(shard.num_tokens, dtype=torch.int32, pin_memory=True)
     h_words.copy_(words_dev)
-    h_z = torch.empty(shard.num_tokens, dtype=torch.int32, pin_memory=True)
+    h_z = torch.empty(shard.num_tokens, dtype=torch.uint16, pin_memory=True)   # topics in the device's own width
     del words_dev, lengths
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
@@ -257,33 +291,31 @@ def b200_arm(args):
     # ---- sampler on torch's current stream so torch CUDA events bracket its kernels --------------
     # (a dedicated non-default stream: the legacy default stream has handle 0, which the C ABI
     # reads as "create a private stream")
+    from ldagibbssampling_b200 import _capi
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     s = L.Sampler(K, V, ALPHA_K * K, BETA, seed=args.seed,
                   mode=L.MODE_LIVE if args.mode == "live" else L.MODE_DEFERRED, device=local_rank,
                   rank=rank, world_size=world, global_token_offset=shard.token_begin,
                   global_doc_offset=shard.doc_begin, stream=stream.cuda_stream)
+    if world > 1:
+        # the exchange is the library's own: its NCCL communicator from a unique id that travels
+        # through torch.distributed (plumbing); torch's NCCL is not on the data path
+        box = [_capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        s.comm_init(box[0])
     s.load_corpus_raw(shard.num_docs, h_doc_ptr.data_ptr(), h_words.data_ptr(), shard.num_tokens)
     s.init_assignments(None)
-    ex = None
-    if world > 1:
-        ptr, n = s.exchange_buffer()
-        ex = torch.as_tensor(_DevBuf(ptr, n), device=dev)
 
     def sync_counts():
         # every shard counted only its own documents: sum once so all n_wk / n_k replicas are global
-        if ex is not None:
-            s.counts_sync_begin()
-            dist.all_reduce(ex, op=dist.ReduceOp.SUM)
-            s.counts_sync_end()
+        if world > 1:
+            _capi.group_sync_counts([s])
 
     sync_counts()
 
-    def one_sweep():
-        s.sweep_begin()
-        if ex is not None:
-            dist.all_reduce(ex, op=dist.ReduceOp.SUM)
-        s.sweep_end()
+    def sweeps(n):
+        _capi.group_sweep([s], n)   # n whole sweeps enqueued back to back (tables, sampling, exchange), one sync at the end
 
     def fence():
         torch.cuda.synchronize()
@@ -291,31 +323,33 @@ def b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_sweep()
-    fence()
-    s.reset_stats()
-    launches0 = s.stats()["kernel_launches"]
+    def timed_block(n):
+        """n sweeps between two events on the sampler's stream, barrier + synchronize on both sides;
+        returns (ms, stats of the block), max over ranks."""
+        fence()
+        s.reset_stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        ev0.record(stream)
+        sweeps(n)
+        ev1.record(stream)
+        fence()
+        st = s.stats()
+        t = torch.tensor([ev0.elapsed_time(ev1), st["cum_sample_ms"], st["cum_tables_ms"], st["cum_finish_ms"]],
+                         dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()], st
 
+    sweeps(args.warmup)
+    fence()
+    launches0 = s.stats()["kernel_launches"]
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        one_sweep()
-    ev1.record(stream)
-    fence()
-    ms_total = ev0.elapsed_time(ev1)
+    (ms_total, cum_sample_ms, cum_tables_ms, cum_finish_ms), st = timed_block(args.steps)
     clk = clocks.stop() if rank == 0 else None
-    st = s.stats()
-
-    t = torch.tensor([ms_total, st["cum_sample_ms"], st["cum_tables_ms"], st["cum_finish_ms"]],
-                     dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, cum_sample_ms, cum_tables_ms, cum_finish_ms = [float(x) for x in t.tolist()]
+    launches = s.stats()["kernel_launches"] - launches0
     value = N_global * args.steps / (ms_total / 1e3)
 
     # ---- LL/token after the timed sweeps (doc parts summed over shards) --------------------------
@@ -359,21 +393,58 @@ def b200_arm(args):
                 "mean_doc_topics": kd, "moved_frac": f_moved, "prior_frac": f_prior,
                 "kernel_share_of_step": cum_sample_ms / ms_total,
                 "tables_ms": cum_tables_ms / max(1, st["cum_sweeps"]),
-                "finish_ms": cum_finish_ms / max(1, st["cum_sweeps"])}
-    launches = st["kernel_launches"] - launches0
+                "finish_ms": cum_finish_ms / max(1, st["cum_sweeps"]),
+                "table_refresh": st["table_refresh_last"], "hot_words": st["hot_words"],
+                "prior_rows_rebuilt_last_sweep": st["rows_refreshed_last"]}
+
+    # ---- count invariants on every rank, on the device (north star: sum n_wk = sum n_dk = N) ----
+    def invariants():
+        sum_nk, sum_nwk, bad_cols, sum_ndk = s.check_invariants()
+        ok = sum_nk == N_global and sum_nwk == N_global and bad_cols == 0 and sum_ndk == shard.num_tokens
+        nk_t = torch.from_numpy(s.nk().astype(np.int64)).to(dev)
+        flags = torch.tensor([0 if ok else 1], dtype=torch.int64, device=dev)
+        if world > 1:   # every replica must hold the same n_k
+            lo, hi = nk_t.clone(), nk_t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not bool((lo == hi).all()):
+                flags += 1
+            dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+        return int(flags.item()) == 0
+
+    invariants_ok = invariants()
+
+    # ---- steady block: the same measurement further into the chain (a 1000-iteration estimate()
+    # spends its time there, not in the first 25 sweeps from a uniform random init) ----------------
+    steady = None
+    done = args.warmup + args.steps
+    if args.after_sweeps > done:
+        sweeps(args.after_sweeps - done)
+        (ms2, samp2, _, _), st2 = timed_block(args.steps)
+        n2 = max(1, shard.num_tokens * st2["cum_sweeps"])
+        steady = {"after_sweeps": args.after_sweeps, "steps": args.steps, "value": N_global * args.steps / (ms2 / 1e3),
+                  "unit": "tokens/s", "ms_per_step": ms2 / args.steps, "kernel_ms": samp2 / max(1, st2["cum_sweeps"]),
+                  "mean_doc_topics": st2["cum_doc_topics"] / n2, "moved_frac": st2["cum_tokens_moved"] / n2,
+                  "prior_frac": st2["cum_prior_bucket"] / n2}
+        dpt, wpt = s.loglik_parts()
+        t = torch.tensor([dpt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        steady["ll_per_token"] = (float(t.item()) + wpt) / N_global
+        invariants_ok = invariants() and invariants_ok
 
     # ---- end to end through the C ABI with HOST buffers: corpus + topics in, one sweep, topics out
-    s.assignments_raw(h_z.data_ptr())  # current chain state, host side
+    s.assignments_u16_raw(h_z.data_ptr())  # current chain state, host side
     fence()
     e2e_times = []
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         fence()
         t0 = time.perf_counter()
         s.load_corpus_raw(shard.num_docs, h_doc_ptr.data_ptr(), h_words.data_ptr(), shard.num_tokens)
-        s.init_assignments_raw(h_z.data_ptr())
+        s.init_assignments_u16_raw(h_z.data_ptr())
         sync_counts()
-        one_sweep()
-        s.assignments_raw(h_z.data_ptr())
+        sweeps(1)
+        s.assignments_u16_raw(h_z.data_ptr())
         fence()
         if i > 0:  # first repetition warms the path
             e2e_times.append(time.perf_counter() - t0)
@@ -381,17 +452,29 @@ def b200_arm(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
-    h2d = 8 * (shard.num_docs + 1) + 4 * shard.num_tokens + 4 * shard.num_tokens
-    d2h = 4 * shard.num_tokens
+    h2d = 8 * (shard.num_docs + 1) + 4 * shard.num_tokens + 2 * shard.num_tokens
+    d2h = 2 * shard.num_tokens
     e2e = {"value": (N_global / e2e_s) if e2e_s > 0 else None, "unit": "tokens/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
-           "call": "b200lda_load_corpus + b200lda_init_assignments(z) + sweep_begin/all-reduce/sweep_end "
-                   "+ b200lda_get_assignments, pinned host buffers, per rank shard"}
+           "call": "b200lda_load_corpus + b200lda_init_assignments_u16(z) + (count sync) + b200lda_group_sweep(1) "
+                   "+ b200lda_get_assignments_u16, pinned host buffers, per rank shard"}
 
     cpu = None
+    ll_same_corpus = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, _, info = run_cpu(args.workload, K, args.cpu_docs, warmup=1, seconds=args.cpu_seconds)
-        cpu = {"value": v, "unit": "tokens/s", **{k: info[k] for k in ("cores", "kind", "sample")}}
+        cpu = {"value": v, "unit": "tokens/s", **{k: info[k] for k in ("cores", "kind", "sample", "runs", "java", "mallet_jar")}}
+        # LL/token of both sides on the SAME corpus (the CPU sample), same initial topics, same sweep count
+        cdp, ctok, cV, cK, cz0 = info["corpus"]
+        t1 = info["runs"][0]
+        g = L.Sampler(cK, cV, ALPHA_K * cK, BETA, seed=7, mode=L.MODE_LIVE if args.mode == "live" else L.MODE_DEFERRED,
+                      device=local_rank)
+        g.load_corpus(cdp, ctok)
+        g.init_assignments(cz0)
+        g.sweep(t1["ll_after_sweeps"])
+        ll_same_corpus = {"corpus": f"the CPU baseline's {args.cpu_docs}-document sample", "sweeps": t1["ll_after_sweeps"],
+                          "cpu_port_T1": t1["ll_per_token"], "b200": g.loglik() / len(ctok)}
+        g.close()
 
     if rank == 0:
         line = {
@@ -401,11 +484,12 @@ def b200_arm(args):
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "docs": D, "tokens": N_global, "V": V, "K": K,
                        "alpha_k": ALPHA_K, "beta": BETA, "mode": args.mode,
-                       "parallelism": f"ad-lda docs/{world} + int32 all-reduce of n_wk/n_k delta per sweep",
+                       "parallelism": f"ad-lda docs/{world} + in-place int32 all-reduce of the n_wk/n_k replica per sweep (library NCCL)",
                        "l2": "inputs exceed L2 (no flush needed)" if 4 * N_global / world > 256e6 else "inputs fit L2",
                        "corpus_gen_s": gen_s},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "ll_per_token": ll_per_token,
+            "cpu_baseline": cpu, "ll_per_token": ll_per_token, "ll_same_corpus": ll_same_corpus,
+            "invariants_ok": bool(invariants_ok), "steady": steady,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

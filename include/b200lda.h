@@ -213,6 +213,12 @@ int b200lda_infer(b200lda_ctx* ctx, int64_t num_docs, const int64_t* doc_ptr, co
 int b200lda_loglik(b200lda_ctx* ctx, double* out);
 int b200lda_loglik_parts(b200lda_ctx* ctx, double* doc_part, double* word_part);
 
+/* Count conservation, checked on the device (north star: sum n_wk = sum n_dk = token count):
+ * out[0] = sum_k n_k, out[1] = sum n_wk, out[2] = number of topics whose n_wk column sum differs
+ * from n_k (must be 0), out[3] = sum of this shard's n_dk. With shards, out[0] and out[1] are
+ * global token counts (every replica holds the global counts), out[3] the shard's own tokens. */
+int b200lda_check_invariants(b200lda_ctx* ctx, int64_t* out /* 4 */);
+
 /* model.data.get(d).topicSequence.getFeatures()            cmu_ron/TrainAndPredict.java:135-143 */
 int b200lda_get_assignments(b200lda_ctx* ctx, int32_t* z /* num_tokens, document order */);
 int b200lda_get_assignments_u16(b200lda_ctx* ctx, uint16_t* z /* num_tokens, document order */);

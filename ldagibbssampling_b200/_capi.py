@@ -90,6 +90,7 @@ SYMBOLS = [
     ("b200lda_sample_frozen", C.c_int, [_P, _P, C.c_uint32, _P]),
     ("b200lda_loglik", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("b200lda_loglik_parts", C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("b200lda_check_invariants", C.c_int, [_P, _P]),
     ("b200lda_get_assignments", C.c_int, [_P, _P]),
     ("b200lda_get_assignments_u16", C.c_int, [_P, _P]),
     ("b200lda_get_nwk", C.c_int, [_P, _P]),
@@ -272,6 +273,12 @@ class Sampler:
         a, b = C.c_double(), C.c_double()
         self._check(self._lib.b200lda_loglik_parts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def check_invariants(self):
+        """(sum n_k, sum n_wk, #topics with column sum != n_k, sum of this shard's n_dk), computed on the device."""
+        out = np.zeros(4, np.int64)
+        self._check(self._lib.b200lda_check_invariants(self._h, _ptr(out)))
+        return tuple(int(x) for x in out)
 
     def assignments(self, dtype=np.int32):
         z = np.empty(self.num_tokens, dtype)

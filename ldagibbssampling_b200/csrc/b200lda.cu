@@ -1492,6 +1492,32 @@ int b200lda_loglik(b200lda_ctx* c, double* out) {
   return B200LDA_OK;
 }
 
+int b200lda_check_invariants(b200lda_ctx* c, int64_t* out) {
+  TRY(enter(c));
+  TRY(need_ready(c));
+  if (!out) return fail(B200LDA_EINVAL, "null argument");
+  const DeviceCorpus& cp = c->corp;
+  const size_t VK = (size_t)c->V * c->K;
+  TRY(ensure_stage(c, sizeof(int32_t) * (size_t)c->K + 4 * sizeof(unsigned long long) + 16));
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_stage);
+  int32_t* d_col = reinterpret_cast<int32_t*>(d_out + 4);
+  CU(cudaMemsetAsync(c->d_stage, 0, 4 * sizeof(unsigned long long) + sizeof(int32_t) * (size_t)c->K, c->stream));
+  const int rows_per_block = 256;
+  dim3 grid((c->K + 255) / 256, (c->V + rows_per_block - 1) / rows_per_block);
+  k_col_sums<<<grid, 256, 0, c->stream>>>(c->V, c->K, rows_per_block, c->d_nwk, d_col);
+  k_check_nk<<<(c->K + 255) / 256, 256, 0, c->stream>>>(c->K, c->d_nk, d_col, d_out);
+  k_sum_i32<<<grid_for(c, (int64_t)VK, 256), 256, 0, c->stream>>>(VK, c->d_nwk, d_out + 1);
+  if (cp.D > 0)
+    k_sum_rows<<<grid_for(c, cp.D * 32, 256), 256, 0, c->stream>>>(cp.D, cp.d_row_ptr, cp.d_row_nnz, cp.d_rows, d_out + 3);
+  c->launches += 4;
+  CU(cudaGetLastError());
+  unsigned long long h[4];
+  CU(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; ++i) out[i] = (int64_t)h[i];
+  return B200LDA_OK;
+}
+
 int b200lda_get_assignments(b200lda_ctx* c, int32_t* z) {
   TRY(enter(c));
   TRY(need_ready(c));

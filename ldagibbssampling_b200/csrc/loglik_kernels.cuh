@@ -165,4 +165,35 @@ k_phi(int V, int K, int k0, int k1, const int32_t* __restrict__ nwk, const int32
   }
 }
 
+// Count invariants (b200lda_check_invariants): out[0] += sum of n_k, out[2] += #topics whose n_wk
+// column sum differs from n_k; out[1] += sum of n_wk; out[3] += sum of the packed n_dk counts.
+__global__ void k_check_nk(int K, const int32_t* __restrict__ nk, const int32_t* __restrict__ colsum,
+                           unsigned long long* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  atomicAdd(out + 0, (unsigned long long)(long long)nk[k]);
+  if (nk[k] != colsum[k]) atomicAdd(out + 2, 1ull);
+}
+__global__ void k_sum_i32(size_t n, const int32_t* __restrict__ x, unsigned long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += x[i];
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+}
+__global__ void k_sum_rows(int64_t D, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ row_nnz,
+                           const uint32_t* __restrict__ rows, unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long acc = 0;
+  for (int64_t d = gw; d < D; d += nw) {
+    const int64_t rp = row_ptr[d];
+    const int nnz = row_nnz[d];
+    for (int j = lane; j < nnz; j += 32) acc += rows[rp + j] & 0xffffu;
+  }
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0 && acc) atomicAdd(out, acc);
+}
+
 }  // namespace b200lda

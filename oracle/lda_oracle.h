@@ -122,6 +122,8 @@ int mallet_add_instances(mallet_model* m, int64_t D, int32_t V, const int64_t* d
                          const int32_t* tok_word, const int32_t* z_init);
 /* estimate(): n iterations, hyper-parameter optimisation off (optimizeInterval = 0). */
 int mallet_estimate(mallet_model* m, int32_t iterations);
+/* cumulative wall-clock seconds of estimate(): worker set-up, sampling phase, merge (T > 1) */
+void mallet_get_timers(const mallet_model* m, double* setup_s, double* sample_s, double* merge_s);
 double mallet_model_log_likelihood(const mallet_model* m);
 void mallet_get_assignments(const mallet_model* m, int32_t* z);
 void mallet_get_counts(const mallet_model* m, int32_t* nwk /*V*K dense*/, int32_t* nk);

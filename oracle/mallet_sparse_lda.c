@@ -1,3 +1,4 @@
+#define _POSIX_C_SOURCE 200809L
 /*
  * oracle/mallet_sparse_lda.c — TEST INFRASTRUCTURE (CPU oracle, part a). PARITY UNPINNED (see
  * lda_oracle.h): restated from Mallet 2.0.7's published algorithm (SURVEY.md Appendix A,
@@ -44,7 +45,16 @@ struct mallet_model {
   int32_t num_threads;
   int32_t random_seed; /* -1 = clock */
   java_random random;
+  /* wall-clock split of estimate(): building the worker replicas, the (parallel) sampling phase,
+   * the serial sumTypeTopicCounts + copy-back. Reported by bench.py's CPU baseline. */
+  double t_setup, t_sample, t_merge;
 };
+
+static double now_seconds(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 typedef struct {
   mallet_model* m;
@@ -385,7 +395,14 @@ static void sum_type_topic_counts(mallet_model* m, worker* ws, int32_t T) {
   }
 }
 
+void mallet_get_timers(const mallet_model* m, double* setup_s, double* sample_s, double* merge_s) {
+  *setup_s = m->t_setup;
+  *sample_s = m->t_sample;
+  *merge_s = m->t_merge;
+}
+
 int mallet_estimate(mallet_model* m, int32_t iterations) {
+  const double t_enter = now_seconds();
   const int32_t T = m->num_threads;
   worker* ws = (worker*)calloc((size_t)T, sizeof(worker));
   const int64_t docs_per_thread = m->D / T;
@@ -421,13 +438,19 @@ int mallet_estimate(mallet_model* m, int32_t iterations) {
     }
   }
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)T);
+  m->t_setup += now_seconds() - t_enter;
   for (int32_t it = 1; it <= iterations; ++it) {
+    const double t0 = now_seconds();
     if (T > 1) {
       for (int32_t t = 0; t < T; ++t) pthread_create(&th[t], NULL, worker_run, &ws[t]);
       for (int32_t t = 0; t < T; ++t) pthread_join(th[t], NULL);
+      const double t1 = now_seconds();
       sum_type_topic_counts(m, ws, T);
+      m->t_sample += t1 - t0;
+      m->t_merge += now_seconds() - t1;
     } else {
       worker_run(&ws[0]);
+      m->t_sample += now_seconds() - t0;
     }
   }
   free(th);

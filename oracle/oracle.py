@@ -92,6 +92,8 @@ def lib():
     L.mallet_add_instances.argtypes = [C.c_void_p, C.c_int64, C.c_int32, _i64p, _i32p, C.c_void_p]
     L.mallet_estimate.restype = C.c_int
     L.mallet_estimate.argtypes = [C.c_void_p, C.c_int32]
+    L.mallet_get_timers.restype = None
+    L.mallet_get_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mallet_model_log_likelihood.restype = C.c_double
     L.mallet_model_log_likelihood.argtypes = [C.c_void_p]
     L.mallet_get_assignments.argtypes = [C.c_void_p, _i32p]
@@ -347,6 +349,12 @@ class MalletModel:
 
     def model_log_likelihood(self):
         return float(self._L.mallet_model_log_likelihood(self._h))
+
+    def timers(self):
+        """Cumulative wall-clock seconds of estimate(): (worker set-up, sampling phase, merge)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._L.mallet_get_timers(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
     def num_tokens(self):
         return int(self._L.mallet_num_tokens(self._h))
