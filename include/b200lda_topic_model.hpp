@@ -151,7 +151,9 @@ class ParallelTopicModel {
   void setNumIterations(int n) { numIterations = n; }
   void setBurninPeriod(int n) { burninPeriod = n; }
   void setOptimizeInterval(int n) { optimizeInterval = n; }
-  void setNumThreads(int n) { numThreads = std::max(1, n); }  // = AD-LDA shards = GPUs (devices 0..n-1 unless setDevices)
+  /** = AD-LDA shards = GPUs (devices 0..n-1 unless setDevices). The reference calls it AFTER
+   *  addInstances (cmu_ron/TrainAndPredict.java:162-164): estimate() re-shards, keeping the chain. */
+  void setNumThreads(int n) { numThreads = std::max(1, n); }
   void setRandomSeed(int seed) { randomSeed = seed; }
   void setTopicDisplay(int interval, int n) { showTopicsInterval = interval; wordsPerTopic = n; }
   void setDevices(const std::vector<int>& devices) { devices_ = devices; }
@@ -181,25 +183,18 @@ class ParallelTopicModel {
   /** estimate(): numIterations sweeps; Mallet's hyper-parameter schedule when optimizeInterval != 0. */
   void estimate() {
     if (ctx_.empty()) throw std::logic_error("addInstances must be called before estimate");
+    if ((int)ctx_.size() != numThreads) rebuild(pullTopics());  // setNumThreads after addInstances
     const bool optimizing = optimizeInterval != 0 && numIterations > burninPeriod;
     const int n = (int)ctx_.size();
-    if (n == 1 && !optimizing) {
-      check(b200lda_sweep(ctx_[0], numIterations));
+    if (!optimizing) {
+      check(b200lda_group_sweep(ctx_.data(), n, numIterations));  // the library drives every shard and the exchange
     } else {
-      if (optimizing) {
-        int width = 1;
-        for (size_t d = 0; d + 1 < docPtr_.size(); ++d) width = std::max(width, (int)(docPtr_[d + 1] - docPtr_[d]) + 1);
-        for (auto* c : ctx_) check(b200lda_hyper_begin(c, width));
-      }
+      int width = 1;
+      for (size_t d = 0; d + 1 < docPtr_.size(); ++d) width = std::max(width, (int)(docPtr_[d + 1] - docPtr_[d]) + 1);
+      for (auto* c : ctx_) check(b200lda_hyper_begin(c, width));
       for (int iteration = 1; iteration <= numIterations; ++iteration) {
-        if (n == 1) {
-          check(b200lda_sweep(ctx_[0], 1));
-        } else {
-          for (auto* c : ctx_) check(b200lda_sweep_begin(c));
-          check(b200lda_group_allreduce(ctx_.data(), n, B200LDA_BUFFER_EXCHANGE));
-          for (auto* c : ctx_) check(b200lda_sweep_end(c));
-        }
-        if (!optimizing || iteration <= burninPeriod) continue;
+        check(b200lda_group_sweep(ctx_.data(), n, 1));
+        if (iteration <= burninPeriod) continue;
         if (iteration % saveSampleInterval == 0)
           for (auto* c : ctx_) check(b200lda_hyper_collect(c));
         if (iteration % optimizeInterval == 0) {
@@ -218,6 +213,58 @@ class ParallelTopicModel {
     }
     sweepsDone_ += numIterations;
     pushTopicsToData(pullTopics());
+  }
+
+  /** Checkpoint (the reference serialises the model and skips training when the file exists,
+   *  cmu_ron/TrainAndPredict.java:179-200, 215-226): configuration, corpus and one library state
+   *  blob per shard (alpha, beta, Philox seed, sweep counter, z). read() needs the same
+   *  InstanceList again (the reference keeps its pipe for that) and continues the chain. */
+  void write(const std::string& file) {
+    std::ofstream out(file, std::ios::binary);
+    auto put = [&](const void* p, size_t n) { out.write(static_cast<const char*>(p), (std::streamsize)n); };
+    const int32_t head[8] = {0x4c324d42, 1, numTopics, numTypes, numThreads, samplingMode, randomSeed, (int32_t)ctx_.size()};
+    put(head, sizeof(head));
+    put(&alphaSum, sizeof(alphaSum));
+    put(&beta, sizeof(beta));
+    put(&sweepsDone_, sizeof(sweepsDone_));
+    for (auto* c : ctx_) {
+      int64_t bytes = 0;
+      check(b200lda_state_size(c, &bytes));
+      std::vector<char> blob((size_t)bytes);
+      check(b200lda_get_state(c, blob.data(), bytes));
+      put(&bytes, sizeof(bytes));
+      put(blob.data(), blob.size());
+    }
+    if (!out) throw std::runtime_error("cannot write " + file);
+  }
+
+  void read(const std::string& file, const InstanceList& training) {
+    std::ifstream in(file, std::ios::binary);
+    auto get = [&](void* p, size_t n) {
+      in.read(static_cast<char*>(p), (std::streamsize)n);
+      if (!in) throw std::runtime_error("truncated model file " + file);
+    };
+    int32_t head[8];
+    get(head, sizeof(head));
+    if (head[0] != 0x4c324d42 || head[1] != 1) throw std::runtime_error("not a b200lda model file: " + file);
+    if (head[2] != numTopics) throw std::invalid_argument("model file has another number of topics");
+    numThreads = head[4];
+    samplingMode = head[5];
+    randomSeed = head[6];
+    get(&alphaSum, sizeof(alphaSum));
+    get(&beta, sizeof(beta));
+    get(&sweepsDone_, sizeof(sweepsDone_));
+    std::vector<std::vector<char>> blobs((size_t)head[7]);
+    for (auto& b : blobs) {
+      int64_t bytes = 0;
+      get(&bytes, sizeof(bytes));
+      b.resize((size_t)bytes);
+      get(b.data(), b.size());
+    }
+    restore_ = std::move(blobs);
+    addInstances(training);  // shards the corpus as before and installs the blobs instead of fresh topics
+    check(b200lda_get_alpha(ctx_[0], alpha.data()));
+    alphaSum = std::accumulate(alpha.begin(), alpha.end(), 0.0);
   }
 
   /** theta_k = (n_dk + alpha_k) / (L_d + alphaSum)   (cmu_ron/TrainAndPredict.java:143) */
@@ -305,6 +352,7 @@ class ParallelTopicModel {
   std::vector<int64_t> shardDoc_;
   std::vector<int> devices_;
   int64_t sweepsDone_ = 0;
+  std::vector<std::vector<char>> restore_;  // read(): one state blob per shard, consumed by rebuild()
 
   std::vector<int32_t> pullTopics() {
     std::vector<int32_t> z(tokens_.size());
@@ -359,6 +407,10 @@ class ParallelTopicModel {
       std::vector<int64_t> dp;
       for (int64_t d = shardDoc_[(size_t)r]; d <= shardDoc_[(size_t)r + 1]; ++d) dp.push_back(docPtr_[(size_t)d] - shardTok_[(size_t)r]);
       check(b200lda_load_corpus(c, (int64_t)dp.size() - 1, dp.data(), tokens_.data() + shardTok_[(size_t)r]));
+      if (restore_.size() == (size_t)world) {
+        check(b200lda_set_state(c, restore_[(size_t)r].data(), (int64_t)restore_[(size_t)r].size()));
+        continue;
+      }
       check(b200lda_init_assignments(c, nullptr));
       const int64_t n = shardTok_[(size_t)r + 1] - shardTok_[(size_t)r];
       const int64_t keep = std::min<int64_t>(shardTok_[(size_t)r + 1], (int64_t)kept.size()) - shardTok_[(size_t)r];
@@ -370,10 +422,17 @@ class ParallelTopicModel {
       }
       check(b200lda_set_sweep_counter(c, sweepsDone_));
     }
-    if (world > 1) {  // every shard counted its own documents only: sum once (sumTypeTopicCounts at start-up)
-      for (auto* c : ctx_) check(b200lda_counts_sync_begin(c));
-      check(b200lda_group_allreduce(ctx_.data(), world, B200LDA_BUFFER_EXCHANGE));
-      for (auto* c : ctx_) check(b200lda_counts_sync_end(c));
+    restore_.clear();
+    if (world > 1) {
+      // one GPU per shard: NCCL communicators inside the library; several shards on one GPU
+      // (tests): the group calls fall back to peer copies
+      bool distinct = true;
+      for (int a = 0; a < world; ++a)
+        for (int b = a + 1; b < world; ++b)
+          distinct = distinct && (devices_.empty() ? a != b : devices_.at((size_t)a) != devices_.at((size_t)b));
+      if (distinct) check(b200lda_group_comm_init(ctx_.data(), world));
+      // every shard counted its own documents only: sum once (sumTypeTopicCounts at start-up)
+      check(b200lda_group_sync_counts(ctx_.data(), world));
       for (auto* c : ctx_) check(b200lda_synchronize(c));
     }
     pushTopicsToData(pullTopics());

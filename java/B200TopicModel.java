@@ -78,6 +78,18 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   private static final MethodHandle GET_BETA = fn("b200lda_get_beta", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   private static final MethodHandle SET_SWEEP_COUNTER =
       fn("b200lda_set_sweep_counter", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
+  // setNumThreads(n) = n shards = n contexts driven by this thread through the library's group calls
+  private static final MethodHandle GROUP_COMM_INIT =
+      fn("b200lda_group_comm_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+  private static final MethodHandle GROUP_SYNC_COUNTS =
+      fn("b200lda_group_sync_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+  private static final MethodHandle GROUP_SWEEP =
+      fn("b200lda_group_sweep", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+  private static final MethodHandle GROUP_ALLREDUCE =
+      fn("b200lda_group_allreduce", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+  private static final MethodHandle LOGLIK_PARTS =
+      fn("b200lda_loglik_parts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+  private static final MethodHandle DEVICE_COUNT = fn("b200lda_device_count", FunctionDescriptor.of(JAVA_INT));
 
   private static void check(int rc) {
     if (rc == 0) return;
@@ -106,7 +118,10 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   public int numIterations = 1000, burninPeriod = 200, optimizeInterval = 50, showTopicsInterval = 50,
       wordsPerTopic = 7, numThreads = 1, randomSeed = -1, saveSampleInterval = 10;
 
-  private transient MemorySegment ctx = MemorySegment.NULL;
+  private transient MemorySegment ctx = MemorySegment.NULL;   // shard 0 (the replica outputs are read from)
+  private transient MemorySegment[] ctxs = {};                // one context per shard = per GPU
+  private transient MemorySegment ctxArray = MemorySegment.NULL;  // the same handles as a C array for the group calls
+  private transient long[] shardTok = {0}, shardDoc = {0};    // token / document offset of every shard (+ total)
   private transient Arena arena;
   private long[] docPtr = {0};
   private int[] tokens = {};
@@ -129,7 +144,9 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   public void setNumIterations(int n) { numIterations = n; }
   public void setBurninPeriod(int n) { burninPeriod = n; }
   public void setOptimizeInterval(int n) { optimizeInterval = n; }   // optimizeAlpha / optimizeBeta every n sweeps
-  public void setNumThreads(int n) { numThreads = Math.max(1, n); }  // = AD-LDA shards = GPUs
+  /** = AD-LDA shards = GPUs (devices 0..n-1). The reference calls it after addInstances
+   *  (cmu_ron/TrainAndPredict.java:164): estimate() re-shards and keeps the chain. */
+  public void setNumThreads(int n) { numThreads = Math.max(1, n); }
   public void setRandomSeed(int seed) { randomSeed = seed; }
   public void setTopicDisplay(int interval, int n) { showTopicsInterval = interval; wordsPerTopic = n; }
   public Alphabet getAlphabet() { return alphabet; }
@@ -154,56 +171,79 @@ public class B200TopicModel implements Serializable, AutoCloseable {
       docPtr[++d] = pos;
       data.add(new TopicAssignment(inst, new LabelSequence(topicAlphabet, new int[fs.getLength()])));
     }
-    int[] kept = topics;
-    rebuildContext();
-    // documents already in the model keep their chain (updateModel, cmu_ron/TrainAndPredict.java:173-177)
-    try (Arena a = Arena.ofConfined()) {
-      MemorySegment z = a.allocate(JAVA_INT, Math.max(1, tokens.length));
-      check((int) INIT_ASSIGNMENTS.invokeExact(ctx, MemorySegment.NULL));
-      if (kept.length > 0) {
-        check((int) GET_ASSIGNMENTS.invokeExact(ctx, z));
-        MemorySegment.copy(kept, 0, z, JAVA_INT, 0, kept.length);
-        check((int) INIT_ASSIGNMENTS.invokeExact(ctx, z));
-      }
-    } catch (RuntimeException | Error e) {
-      throw e;
-    } catch (Throwable t) {
-      throw new RuntimeException(t);
-    }
+    rebuildContexts(topics);   // documents already in the model keep their chain (updateModel, cmu_ron/TrainAndPredict.java:173-177)
     pullTopics();
   }
 
-  private void rebuildContext() {
+  /** Contiguous document ranges balanced by tokens, one context per range on device r. kept =
+   *  topics of the documents already sampled (document order); new documents get the Philox draw. */
+  private void rebuildContexts(int[] kept) {
     close();
     arena = Arena.ofShared();
     try {
-      MemorySegment cfg = arena.allocate(CONFIG);
-      cfg.set(JAVA_INT, 0, (int) CONFIG.byteSize());
-      cfg.set(JAVA_INT, 4, numTopics);
-      cfg.set(JAVA_INT, 8, Math.max(1, numTypes));
-      cfg.set(JAVA_INT, 12, 0 /* B200LDA_MODE_LIVE */);
-      cfg.set(JAVA_DOUBLE, 16, alphaSum);
-      cfg.set(JAVA_DOUBLE, 24, beta);
+      final int world = numThreads;
+      final int docs = docPtr.length - 1;
+      final long total = docPtr[docs];
+      shardDoc = new long[world + 1];
+      for (int r = 1; r < world; r++) {
+        int d = Arrays.binarySearch(docPtr, 0, docs, total * r / world);
+        if (d < 0) d = -d - 1;
+        shardDoc[r] = Math.min(Math.max(d, shardDoc[r - 1]), docs);
+      }
+      shardDoc[world] = docs;
+      shardTok = new long[world + 1];
+      for (int r = 0; r <= world; r++) shardTok[r] = docPtr[(int) shardDoc[r]];
       if (randomSeed == -1) randomSeed = (int) (System.nanoTime() & 0x7fffffff);  // Mallet: clock seed
-      cfg.set(JAVA_LONG, 32, (long) randomSeed);
-      cfg.set(JAVA_INT, 40, 0);   // device
-      cfg.set(JAVA_INT, 44, 0);   // rank
-      cfg.set(JAVA_INT, 48, 1);   // world_size (multi-GPU: one context per device + NCCL, INTEGRATION.md)
-      cfg.set(JAVA_LONG, 56, 0L);
-      cfg.set(JAVA_LONG, 64, 0L);
-      cfg.set(ADDRESS, 72, MemorySegment.NULL);
-      MemorySegment out = arena.allocate(ADDRESS);
-      check((int) CREATE.invokeExact(cfg, out));
-      ctx = out.get(ADDRESS, 0);
-      MemorySegment a = arena.allocate(JAVA_DOUBLE, numTopics);
-      MemorySegment.copy(alpha, 0, a, JAVA_DOUBLE, 0, numTopics);
-      check((int) SET_ALPHA.invokeExact(ctx, a));
-      MemorySegment dp = arena.allocate(JAVA_LONG, docPtr.length);
-      MemorySegment.copy(docPtr, 0, dp, JAVA_LONG, 0, docPtr.length);
-      MemorySegment tw = arena.allocate(JAVA_INT, Math.max(1, tokens.length));
-      MemorySegment.copy(tokens, 0, tw, JAVA_INT, 0, tokens.length);
-      check((int) LOAD_CORPUS.invokeExact(ctx, (long) (docPtr.length - 1), dp, tw));
-      check((int) SET_SWEEP_COUNTER.invokeExact(ctx, sweepsDone));
+      final int devices = Math.max(1, (int) DEVICE_COUNT.invokeExact());
+      ctxs = new MemorySegment[world];
+      ctxArray = arena.allocate(ADDRESS, world);
+      for (int r = 0; r < world; r++) {
+        MemorySegment cfg = arena.allocate(CONFIG);
+        cfg.set(JAVA_INT, 0, (int) CONFIG.byteSize());
+        cfg.set(JAVA_INT, 4, numTopics);
+        cfg.set(JAVA_INT, 8, Math.max(1, numTypes));
+        cfg.set(JAVA_INT, 12, 0 /* B200LDA_MODE_LIVE */);
+        cfg.set(JAVA_DOUBLE, 16, alphaSum);
+        cfg.set(JAVA_DOUBLE, 24, beta);
+        cfg.set(JAVA_LONG, 32, (long) randomSeed);
+        cfg.set(JAVA_INT, 40, world <= devices ? r : r % devices);   // device
+        cfg.set(JAVA_INT, 44, r);       // rank
+        cfg.set(JAVA_INT, 48, world);   // world_size
+        cfg.set(JAVA_INT, 52, 0);       // table_refresh: auto
+        cfg.set(JAVA_LONG, 56, shardTok[r]);
+        cfg.set(JAVA_LONG, 64, shardDoc[r]);
+        cfg.set(ADDRESS, 72, MemorySegment.NULL);
+        MemorySegment out = arena.allocate(ADDRESS);
+        check((int) CREATE.invokeExact(cfg, out));
+        ctxs[r] = out.get(ADDRESS, 0);
+        ctxArray.setAtIndex(ADDRESS, r, ctxs[r]);
+        MemorySegment a = arena.allocate(JAVA_DOUBLE, numTopics);
+        MemorySegment.copy(alpha, 0, a, JAVA_DOUBLE, 0, numTopics);
+        check((int) SET_ALPHA.invokeExact(ctxs[r], a));
+        final int nd = (int) (shardDoc[r + 1] - shardDoc[r]);
+        final int nt = (int) (shardTok[r + 1] - shardTok[r]);
+        MemorySegment dp = arena.allocate(JAVA_LONG, nd + 1);
+        for (int d = 0; d <= nd; d++) dp.setAtIndex(JAVA_LONG, d, docPtr[(int) shardDoc[r] + d] - shardTok[r]);
+        MemorySegment tw = arena.allocate(JAVA_INT, Math.max(1, nt));
+        MemorySegment.copy(tokens, (int) shardTok[r], tw, JAVA_INT, 0, nt);
+        check((int) LOAD_CORPUS.invokeExact(ctxs[r], (long) nd, dp, tw));
+        check((int) INIT_ASSIGNMENTS.invokeExact(ctxs[r], MemorySegment.NULL));
+        final int keep = (int) (Math.min(shardTok[r + 1], (long) kept.length) - shardTok[r]);
+        if (keep > 0) {
+          MemorySegment z = arena.allocate(JAVA_INT, Math.max(1, nt));
+          check((int) GET_ASSIGNMENTS.invokeExact(ctxs[r], z));
+          MemorySegment.copy(kept, (int) shardTok[r], z, JAVA_INT, 0, keep);
+          check((int) INIT_ASSIGNMENTS.invokeExact(ctxs[r], z));
+        }
+        check((int) SET_SWEEP_COUNTER.invokeExact(ctxs[r], sweepsDone));
+      }
+      ctx = ctxs[0];
+      if (world > 1) {
+        // one GPU per shard: NCCL communicators inside the library; fewer GPUs than shards: the
+        // group calls fall back to peer copies
+        if (world <= devices) check((int) GROUP_COMM_INIT.invokeExact(ctxArray, world));
+        check((int) GROUP_SYNC_COUNTS.invokeExact(ctxArray, world));   // Mallet's sumTypeTopicCounts at start-up
+      }
     } catch (RuntimeException | Error e) {
       throw e;
     } catch (Throwable t) {
@@ -214,21 +254,27 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   /** estimate(): numIterations sweeps on the GPU, then z is written back into every topicSequence. */
   public void estimate() throws IOException {
     try {
+      if (ctxs.length != numThreads) rebuildContexts(topics);   // setNumThreads after addInstances
+      final int world = ctxs.length;
       if (optimizeInterval == 0 || numIterations <= burninPeriod) {
-        check((int) SWEEP.invokeExact(ctx, numIterations));
+        check((int) GROUP_SWEEP.invokeExact(ctxArray, world, numIterations));
       } else {
         // Mallet's schedule: statistics on iterations > burn-in that are multiples of
         // saveSampleInterval, optimizeAlpha + optimizeBeta on multiples of optimizeInterval
         int width = 1;
         for (int d = 0; d + 1 < docPtr.length; d++) width = Math.max(width, (int) (docPtr[d + 1] - docPtr[d]) + 1);
-        check((int) HYPER_BEGIN.invokeExact(ctx, width));
+        for (MemorySegment c : ctxs) check((int) HYPER_BEGIN.invokeExact(c, width));
         for (int iteration = 1; iteration <= numIterations; iteration++) {
-          check((int) SWEEP.invokeExact(ctx, 1));
+          check((int) GROUP_SWEEP.invokeExact(ctxArray, world, 1));
           if (iteration <= burninPeriod) continue;
-          if (iteration % saveSampleInterval == 0) check((int) HYPER_COLLECT.invokeExact(ctx));
+          if (iteration % saveSampleInterval == 0)
+            for (MemorySegment c : ctxs) check((int) HYPER_COLLECT.invokeExact(c));
           if (iteration % optimizeInterval == 0) {
-            check((int) OPTIMIZE_ALPHA.invokeExact(ctx));
-            check((int) OPTIMIZE_BETA.invokeExact(ctx));
+            if (world > 1) check((int) GROUP_ALLREDUCE.invokeExact(ctxArray, world, 1 /* B200LDA_BUFFER_HYPER */));
+            for (MemorySegment c : ctxs) {
+              check((int) OPTIMIZE_ALPHA.invokeExact(c));
+              check((int) OPTIMIZE_BETA.invokeExact(c));
+            }
             try (Arena a = Arena.ofConfined()) {
               MemorySegment al = a.allocate(JAVA_DOUBLE, numTopics), be = a.allocate(JAVA_DOUBLE);
               check((int) GET_ALPHA.invokeExact(ctx, al));
@@ -253,7 +299,9 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   private void pullTopics() {
     try (Arena a = Arena.ofConfined()) {
       MemorySegment z = a.allocate(JAVA_INT, Math.max(1, tokens.length));
-      check((int) GET_ASSIGNMENTS.invokeExact(ctx, z));
+      for (int r = 0; r < ctxs.length; r++)
+        if (shardTok[r + 1] > shardTok[r])
+          check((int) GET_ASSIGNMENTS.invokeExact(ctxs[r], z.asSlice(4L * shardTok[r])));
       topics = z.asSlice(0, 4L * tokens.length).toArray(JAVA_INT);
     } catch (RuntimeException | Error e) {
       throw e;
@@ -277,9 +325,14 @@ public class B200TopicModel implements Serializable, AutoCloseable {
 
   public double modelLogLikelihood() {
     try (Arena a = Arena.ofConfined()) {
-      MemorySegment out = a.allocate(JAVA_DOUBLE);
-      check((int) LOGLIK.invokeExact(ctx, out));
-      return out.get(JAVA_DOUBLE, 0);
+      MemorySegment dp = a.allocate(JAVA_DOUBLE), wp = a.allocate(JAVA_DOUBLE);
+      double doc = 0.0, word = 0.0;   // every shard's document part + the (replicated) word / topic part
+      for (MemorySegment c : ctxs) {
+        check((int) LOGLIK_PARTS.invokeExact(c, dp, wp));
+        doc += dp.get(JAVA_DOUBLE, 0);
+        word = wp.get(JAVA_DOUBLE, 0);
+      }
+      return doc + word;
     } catch (RuntimeException | Error e) {
       throw e;
     } catch (Throwable t) {
@@ -355,10 +408,14 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   }
 
   @Override public void close() {
-    if (ctx != null && !ctx.equals(MemorySegment.NULL)) {
-      try { DESTROY.invokeExact(ctx); } catch (Throwable ignored) { }
-      ctx = MemorySegment.NULL;
-    }
+    if (ctxs != null)
+      for (MemorySegment c : ctxs)
+        if (c != null && !c.equals(MemorySegment.NULL)) {
+          try { DESTROY.invokeExact(c); } catch (Throwable ignored) { }
+        }
+    ctxs = new MemorySegment[0];
+    ctx = MemorySegment.NULL;
+    ctxArray = MemorySegment.NULL;
     if (arena != null) { arena.close(); arena = null; }
   }
 
@@ -367,17 +424,13 @@ public class B200TopicModel implements Serializable, AutoCloseable {
   private void readObject(java.io.ObjectInputStream in) throws IOException, ClassNotFoundException {
     in.defaultReadObject();
     ctx = MemorySegment.NULL;
+    ctxs = new MemorySegment[0];
+    ctxArray = MemorySegment.NULL;
     if (tokens.length > 0 || docPtr.length > 1) {
-      int[] kept = topics;
-      rebuildContext();
-      try (Arena a = Arena.ofConfined()) {
-        MemorySegment z = a.allocate(JAVA_INT, Math.max(1, kept.length));
-        MemorySegment.copy(kept, 0, z, JAVA_INT, 0, kept.length);
-        check((int) INIT_ASSIGNMENTS.invokeExact(ctx, z));
-      } catch (RuntimeException | Error e) {
-        throw e;
-      } catch (Throwable t) {
-        throw new IOException(t);
+      try {
+        rebuildContexts(topics);   // the chain continues from the serialised topics and sweep counter
+      } catch (RuntimeException e) {
+        throw new IOException(e);
       }
     }
   }

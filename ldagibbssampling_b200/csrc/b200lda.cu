@@ -1567,27 +1567,44 @@ int b200lda_get_ndk_csr(b200lda_ctx* c, int64_t* row_ptr, int32_t* topic, int32_
   TRY(need_ready(c));
   if (!row_ptr) return fail(B200LDA_EINVAL, "row_ptr is null");
   const DeviceCorpus& cp = c->corp;
-  std::vector<int32_t> nnz((size_t)cp.D);
-  if (cp.D > 0) CU(cudaMemcpyAsync(nnz.data(), cp.d_row_nnz, sizeof(int32_t) * cp.D, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  row_ptr[0] = 0;
-  for (int64_t d = 0; d < cp.D; ++d) row_ptr[d + 1] = row_ptr[d] + nnz[d];
-  if (!topic || !count) return B200LDA_OK;
-  std::vector<int64_t> h_row_ptr((size_t)cp.D + 1, 0);
-  CU(cudaMemcpyAsync(h_row_ptr.data(), cp.d_row_ptr, sizeof(int64_t) * (cp.D + 1), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  const int64_t cap = h_row_ptr[cp.D];
-  std::vector<uint32_t> rows((size_t)cap);
-  if (cap > 0) CU(cudaMemcpyAsync(rows.data(), cp.d_rows, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  for (int64_t d = 0; d < cp.D; ++d) {
-    const uint32_t* src = rows.data() + h_row_ptr[d];
-    for (int32_t j = 0; j < nnz[d]; ++j) {
-      topic[row_ptr[d] + j] = (int32_t)(src[j] >> 16);
-      count[row_ptr[d] + j] = (int32_t)(src[j] & 0xffffu);
-    }
+  // compact on the device: exclusive scan of the rows' nnz (two-level, as the row planner does),
+  // then one pass that unpacks (topic << 16 | count) into the two output arrays
+  const int64_t nblocks = (cp.D + kScanBlock - 1) / kScanBlock;
+  int64_t* d_ptr = nullptr;
+  int64_t total = 0;
+  if (cp.D > 0) {
+    TRY(ensure_stage(c, sizeof(int64_t) * ((size_t)cp.D + 1 + 2 * (size_t)(nblocks + 1))));
+    d_ptr = reinterpret_cast<int64_t*>(c->d_stage);
+    unsigned long long* d_bsum = reinterpret_cast<unsigned long long*>(d_ptr + cp.D + 1);
+    long long* d_boff = reinterpret_cast<long long*>(d_bsum + nblocks + 1);
+    k_nnz_block_sums<<<(unsigned)nblocks, kScanBlock, 0, c->stream>>>(cp.D, cp.d_row_nnz, d_bsum);
+    k_exclusive_scan_u64<<<1, 1024, 0, c->stream>>>((int)nblocks, d_bsum, d_boff);
+    k_nnz_ptr_apply<<<(unsigned)nblocks, kScanBlock, 0, c->stream>>>(cp.D, cp.d_row_nnz, d_boff, d_ptr);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(row_ptr, d_ptr, sizeof(int64_t) * (cp.D + 1), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    total = row_ptr[cp.D];
+  } else {
+    row_ptr[0] = 0;
   }
-  return B200LDA_OK;
+  if (!topic || !count || total == 0) return B200LDA_OK;
+  int32_t* d_tc = nullptr;  // [topic | count]
+  TRY(dev_alloc_t(c, &d_tc, 2 * (size_t)total));
+  auto done = [&](int code) {
+    c->device_bytes -= (int64_t)(sizeof(int32_t) * 2 * (size_t)total);
+    dev_free(d_tc);
+    return code;
+  };
+  k_unpack_rows<<<grid_for(c, cp.D * 32, 256), 256, 0, c->stream>>>(cp.D, cp.d_row_ptr, cp.d_row_nnz, cp.d_rows, d_ptr, d_tc,
+                                                                   d_tc + total);
+  c->launches += 1;
+  if (cudaGetLastError() != cudaSuccess ||
+      cudaMemcpyAsync(topic, d_tc, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaMemcpyAsync(count, d_tc + total, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return done(fail(B200LDA_ECUDA, "n_dk compaction failed: %s", cudaGetErrorString(cudaGetLastError())));
+  return done(B200LDA_OK);
 }
 
 int b200lda_get_word_order(b200lda_ctx* c, int64_t* word_ptr, int64_t* word_tokens) {
@@ -1817,7 +1834,10 @@ int b200lda_optimize_beta(b200lda_ctx* c) {
     for (int k = 0; k < c->K; ++k)
       if (nk[(size_t)k] > 0) denominator += digamma(beta_sum + (double)nk[(size_t)k]) - base;
     if (!(denominator > 0.0) || !(numerator > 0.0)) return fail(B200LDA_ERANGE, "beta optimisation has no statistics");
-    beta_sum = param * numerator / denominator;
+    const double next = param * numerator / denominator;
+    const bool settled = std::fabs(next - beta_sum) <= 1e-10 * std::fabs(beta_sum);  // Mallet runs all 200 rounds; past
+    beta_sum = next;                                                                  // this point they change nothing
+    if (settled) break;
   }
   if (!(beta_sum > 0.0) || !std::isfinite(beta_sum)) return fail(B200LDA_ERANGE, "beta optimisation diverged");
   c->beta = beta_sum / (double)c->V;

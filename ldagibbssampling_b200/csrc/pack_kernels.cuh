@@ -154,6 +154,45 @@ k_row_ptr_apply(int64_t D, int K, const int64_t* __restrict__ doc_ptr, const lon
   if (d == D - 1) row_ptr[D] = base + ex + v;
 }
 
+// b200lda_get_ndk_csr: compact row offsets = exclusive scan of the rows' nnz (same two-level scan),
+// then the packed (topic << 16 | count) slots unpacked into the caller's two arrays.
+__global__ void __launch_bounds__(kScanBlock)
+k_nnz_block_sums(int64_t D, const int32_t* __restrict__ nnz, unsigned long long* __restrict__ block_sum) {
+  __shared__ long long s_warp[32];
+  const int64_t d = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  long long total;
+  block_exclusive_scan(d < D ? (long long)nnz[d] : 0, s_warp, &total);
+  if (threadIdx.x == 0) block_sum[blockIdx.x] = (unsigned long long)total;
+}
+__global__ void __launch_bounds__(kScanBlock)
+k_nnz_ptr_apply(int64_t D, const int32_t* __restrict__ nnz, const long long* __restrict__ block_off,
+                int64_t* __restrict__ out_ptr) {
+  __shared__ long long s_warp[32];
+  const int64_t d = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const long long v = d < D ? (long long)nnz[d] : 0;
+  long long total;
+  const long long ex = block_exclusive_scan(v, s_warp, &total);
+  const long long base = block_off[blockIdx.x];
+  if (d < D) out_ptr[d] = base + ex;
+  if (d == D - 1) out_ptr[D] = base + ex + v;
+}
+__global__ void k_unpack_rows(int64_t D, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ nnz,
+                              const uint32_t* __restrict__ rows, const int64_t* __restrict__ out_ptr,
+                              int32_t* __restrict__ topic, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t d = gw; d < D; d += nw) {
+    const int64_t rp = row_ptr[d], op = out_ptr[d];
+    const int n = nnz[d];
+    for (int j = lane; j < n; j += 32) {
+      const uint32_t v = rows[rp + j];
+      topic[op + j] = (int32_t)(v >> 16);
+      count[op + j] = (int32_t)(v & 0xffffu);
+    }
+  }
+}
+
 // Document plan, pass 3: visiting order = longest document first. len_start[L] = number of
 // documents longer than L (from the length histogram); ties are ordered by arrival.
 __global__ void k_doc_order_scatter(int64_t D, const int64_t* __restrict__ doc_ptr, const long long* __restrict__ len_start,

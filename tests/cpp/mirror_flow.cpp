@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <memory>
 
 #include "b200lda_topic_model.hpp"
 
@@ -24,15 +25,36 @@ int main(int argc, char** argv) {
     if (!in) throw std::runtime_error("cannot open corpus file");
     InstanceList training = readInverseDocs(in, alphabet);
 
-    ParallelTopicModel model(K, 0.1 * K, 0.01);  // new ParallelTopicModel(K, alphaSum, beta)
-    model.samplingMode = B200LDA_MODE_DEFERRED;
-    model.setRandomSeed(seed);
-    model.setNumThreads(threads);
-    if (threads > 1) model.setDevices(std::vector<int>((size_t)threads, 0));
-    model.addInstances(training);
-    model.setOptimizeInterval(0);
-    model.setNumIterations(iters);
-    model.estimate();
+    // the reference's order (cmu_ron/TrainAndPredict.java:160-166): construct, addInstances, THEN
+    // setOptimizeInterval / setNumThreads / setNumIterations, estimate
+    std::unique_ptr<ParallelTopicModel> first(new ParallelTopicModel(K, 0.1 * K, 0.01));
+    first->samplingMode = B200LDA_MODE_DEFERRED;
+    first->setRandomSeed(seed);
+    first->addInstances(training);
+    first->setOptimizeInterval(0);
+    first->setNumThreads(threads);
+    if (threads > 1) first->setDevices(std::vector<int>((size_t)threads, 0));
+    std::unique_ptr<ParallelTopicModel> resumed;
+    if (argc > 6) {
+      // train half, save, throw the model away, load, train the rest (reference save / load,
+      // cmu_ron/TrainAndPredict.java:179-200): the chain must be the uninterrupted one
+      first->setNumIterations(iters / 2);
+      first->estimate();
+      const std::string path = std::string(argv[6]) + "/model.bin";
+      first->write(path);
+      first->close();
+      first.reset();
+      resumed.reset(new ParallelTopicModel(K, 0.1 * K, 0.01));
+      if (threads > 1) resumed->setDevices(std::vector<int>((size_t)threads, 0));
+      resumed->read(path, training);
+      resumed->setOptimizeInterval(0);
+      resumed->setNumIterations(iters - iters / 2);
+      resumed->estimate();
+    } else {
+      first->setNumIterations(iters);
+      first->estimate();
+    }
+    ParallelTopicModel& model = resumed ? *resumed : *first;
     TopicInferencer inferencer = model.getInferencer();
 
     uint64_t h = 1469598103934665603ull;  // FNV-1a over all topic assignments

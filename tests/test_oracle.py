@@ -350,6 +350,32 @@ def test_inferencers_return_distributions(oracle):
     m.close()
 
 
+def test_spec_inferencer_agrees_with_the_mallet_faithful_one_within_monte_carlo_error(oracle):
+    """TopicInferencer.getSampledDistribution(doc, 100, 10, 10) is a Monte-Carlo estimate of the
+    held-out document's posterior theta: one call is noisy (L1 distance between two seeds ~0.3), so the
+    two implementations are compared through the MEAN over 50 seeds each. The spec inferencer (what
+    the GPU runs, bit for bit) and the Mallet-faithful one must agree within the Monte-Carlo error of
+    those means: L1 distance below 4 standard errors (summed over topics), and well inside the
+    seed-to-seed spread of either side."""
+    D, V, K = 300, 200, 10
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 8)
+    m = oracle.MalletModel(K, ALPHA * K, BETA, seed=5)
+    m.add_instances(dp, tok, V)
+    m.estimate(60)
+    nwk, nk = m.counts()
+    for d in (3, 57, 211):
+        doc = tok[dp[d]:dp[d + 1]].astype(np.int32)
+        hd = np.array([0, len(doc)], np.int64)
+        a = np.array([m.infer(doc, 100, 10, 10, seed=100 + i) for i in range(50)])
+        b = np.array([oracle.spec_infer(hd, doc, nwk, nk, ALPHA, BETA, 100, 10, 10, 200 + i)[0] for i in range(50)])
+        se = np.sqrt(a.var(0, ddof=1) / 50 + b.var(0, ddof=1) / 50)
+        l1 = np.abs(a.mean(0) - b.mean(0)).sum()
+        assert l1 <= 4.0 * se.sum() + 1e-3, (d, l1, se.sum())
+        spread = np.abs(a - a.mean(0)).sum(1).mean()   # a single draw's typical L1 distance from the mean
+        assert l1 < 0.5 * spread, (d, l1, spread)
+    m.close()
+
+
 def test_hyper_parameter_fixed_points_recover_known_parameters(oracle):
     """Dirichlet.learnParameters / learnSymmetricConcentration restatements: digamma against scipy,
     and maximum-likelihood recovery of the parameters that generated the histograms."""
