@@ -372,15 +372,16 @@ int shape_for(b200lda_ctx* c, int max_row, int doc_chunk, int longest, SweepShap
   const size_t tab = sizeof(uint32_t) * (size_t)sweep_table_words(c->K);  // invden, ab, per-CTA n_k delta
   const size_t per_warp = sizeof(uint32_t) * (size_t)sweep_warp_words(c->K, cap_tiles);
   SweepShape best;
-  int best_warps = 0;
+  int best_warps = 0;  // in quarter-warps: tables in global memory count 3/4 (every move then
+                       // pays two global atomics on the K topic totals instead of two shared ones)
   for (int ts = 1; ts >= 0; --ts) {
     for (int wpc = 8; wpc >= 1; wpc >>= 1) {
       const size_t need = (ts ? tab : 0) + per_warp * wpc;
       if (need > kMaxSmemPerCta) continue;
       int occ = 0;
       TRY(occupancy_of(ts != 0, rc, wpc * 32, need, &occ));
-      if (occ * wpc > best_warps) {
-        best_warps = occ * wpc;
+      if (occ * wpc * (ts ? 4 : 3) > best_warps) {
+        best_warps = occ * wpc * (ts ? 4 : 3);
         best.rc = rc;
         best.cap_tiles = cap_tiles;
         best.tables_in_smem = ts != 0;
@@ -412,7 +413,7 @@ int configure_sweep(b200lda_ctx* c, DeviceCorpus& cp, const std::vector<int64_t>
   const int widest = std::min(c->K, std::max(1, cp.max_doc_len));
   std::vector<int> caps;
   for (int rc = 0; rc < kWideClass && rowclass_max_len(rc) < widest; ++rc) caps.push_back(rowclass_max_len(rc));
-  for (int cap = 511; cap < widest; cap = 2 * cap + 1) caps.push_back(cap);
+  for (int cap = 511; cap < widest; cap = 2 * cap + 1) caps.push_back(cap);  // 511 slots = 16 tiles still run 4 CTAs per SM
   caps.push_back(widest);
   auto docs_with_row_above = [&](int cap) -> int64_t {  // rows are min(len, K) slots wide
     if (cap >= c->K || cap + 1 >= (int)len_ge.size()) return 0;

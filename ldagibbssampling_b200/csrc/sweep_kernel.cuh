@@ -125,13 +125,14 @@ __host__ __device__ constexpr int rowclass_min_ctas(int rc) {
 
 // Shared memory (32-bit words). Per CTA: [invden | ab | n_k delta] (3K, rounded to 4, when
 // TABLES_IN_SMEM). Per warp: the token batch (32 tokens x 8 words), the write-back bitmap and its
-// word prefix (2 x ceil(K/32)), and in the wide class the row: slots, weights, lane-local
-// prefixes (32 cap_tiles each) and the tile bounds (cap_tiles).
+// word prefix (2 x ceil(K/32)), and in the wide class the row: slots and lane-local prefixes
+// (32 cap_tiles each) and the tile bounds (cap_tiles); a wide row's weights invden[t] * n_dk are
+// recomputed per use, which keeps 8 warps x 16 tiles + the tables at 4 CTAs per SM.
 constexpr int kBatchWords = 256;
 __host__ __device__ constexpr int bitmap_words(int K) { return (K + 31) >> 5; }
 __host__ __device__ constexpr int sweep_table_words(int K) { return (3 * K + 3) & ~3; }
 __host__ __device__ constexpr int sweep_warp_words(int K, int cap_tiles) {
-  return (kBatchWords + 2 * bitmap_words(K) + 97 * cap_tiles + 3) & ~3;
+  return (kBatchWords + 2 * bitmap_words(K) + 65 * cap_tiles + 3) & ~3;
 }
 
 // The kernel's dynamic shared memory, addressed by WORD OFFSET everywhere: indexing the extern
@@ -197,7 +198,7 @@ struct WarpCtx {
   int batch;   // this warp's token batch
   int bm;      // write-back bitmap, pf = bm + bmw: exclusive popcount prefix per bitmap word
   int bmw;
-  int row;     // wide class: slots at row, weights at row + 32 capT, prefixes at row + 64 capT, bounds at row + 96 capT
+  int row;     // wide class: slots at row, prefixes at row + 32 capT, bounds at row + 64 capT
   int capT;
   bool nkd_in_smem;
   int top_lane;  // offset of this lane's entry of the top search level inside a word's prior block, -1: none
@@ -483,9 +484,9 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
 
 // Wide path: a topic new to the document takes the lowest dead lane of its preferred tile, else of
 // the next tile (cyclically) that has a dead slot, else lane 0 of an appended tile.
-__device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt, float inv_n) {
+__device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt) {
   const int lane = c.lane;
-  const int SV = c.row, WT = c.row + 32 * c.capT, BD = c.row + 96 * c.capT;
+  const int SV = c.row, BD = c.row + 64 * c.capT;
   const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
   int ge = 0;
   for (int g = 1 + lane; g < nt; g += 32) ge += (newt >= (int)smem_u32(BD + g)) ? 1 : 0;
@@ -506,14 +507,12 @@ __device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt,
     gsel = nt;
     msel = 1u;
     smem_u32(SV + (nt << 5) + lane) = 0u;
-    smem_f32(WT + (nt << 5) + lane) = 0.0f;
     if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
     nt += 1;
     __syncwarp();
   }
   if (lane == __ffs(msel) - 1) {
     smem_u32(SV + (gsel << 5) + lane) = nkey;
-    smem_f32(WT + (gsel << 5) + lane) = inv_n;
   }
   __syncwarp();
 }
@@ -523,7 +522,7 @@ template <int MODE, bool LIVE, bool TS>
 __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c, int& nt, int tok) {
   constexpr bool EXCL = MODE != MODE_INFER;
   const int lane = c.lane;
-  const int SV = c.row, WT = c.row + 32 * c.capT, PS = c.row + 64 * c.capT, BD = c.row + 96 * c.capT;
+  const int SV = c.row, PS = c.row + 32 * c.capT;
   const uint4 ta = smem_u128(tok);
   const uint32_t w = LIVE ? ta.x >> 1 : ta.x;
   const int o = (int)ta.y;
@@ -556,7 +555,8 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
         int n = nvg[g];
         if (EXCL && is_old) n -= 1;
         n = max(n, 0);
-        const float wslot = smem_f32(WT + j);
+        const int topic = (int)(svg[g] >> 16);  // dead slot: count 0, weight +0
+        const float wslot = fmul(TS ? smem_f32(c.tab + topic) : __ldg(p.invden + topic), (float)(svg[g] & 0xffffu));
         const float wv = is_old ? fsub(wslot, inv_o) : wslot;
         run = fadd(run, fmul(fadd((float)n, c.beta_f), wv));
         smem_f32(PS + j) = run;
@@ -593,24 +593,18 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
 
   if (MODE != MODE_FROZEN && newt != o) {
     ++c.st_moved;
-    const float inv_n = TS ? smem_f32(c.tab + newt) : __ldg(p.invden + newt);
     const uint32_t nkey = ((uint32_t)newt << 16) + 1u;
     bool has_new = false;
     for (int g = 0; g < nt; ++g) {
       const int j = (g << 5) + lane;
-      uint32_t v = smem_u32(SV + j);
+      const uint32_t v = smem_u32(SV + j);
       const bool io = (v - okey) < 0xffffu;
       const bool in = (v - nkey) < 0xffffu;
-      if (io | in) {
-        v += in ? 1u : 0xffffffffu;
-        const uint32_t cnt = v & 0xffffu;
-        smem_u32(SV + j) = v;
-        smem_f32(WT + j) = fmul(in ? inv_n : inv_o, (float)cnt);
-      }
+      if (io | in) smem_u32(SV + j) = v + (in ? 1u : 0xffffffffu);
       has_new = has_new || in;
     }
     __syncwarp();
-    if (!doc_bucket && !__any_sync(kFullMask, has_new)) wide_insert(c, nt, newt, inv_n);
+    if (!doc_bucket && !__any_sync(kFullMask, has_new)) wide_insert(c, nt, newt);
     count_moves(p, c, write_row<LIVE>(p, nrow, (int)w, c.K), o, newt);
   }
   return newt;
@@ -704,7 +698,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   asm volatile("" : "+r"(c.batch_addr));
   c.row_bytes = 4u * (uint32_t)K;
   asm volatile("" : "+r"(c.row_bytes));
-  const int SV = c.row, WT = c.row + 32 * c.capT, BD = c.row + 96 * c.capT;
+  const int SV = c.row, BD = c.row + 64 * c.capT;
 
   unsigned long long st_moved = 0, st_prior = 0, st_nnz = 0;
   const unsigned long long ndocs = (unsigned long long)(p.order_end - p.order_begin);
@@ -767,15 +761,8 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
         } else {
           for (int g = 0; g < nt; ++g) {
             uint32_t v = 0u;
-            float wv = 0.0f;
-            if (lane < sp.size(g)) {
-              v = p.rows[rp + sp.begin(g) + lane];
-              const int topic = (int)(v >> 16);
-              const float inv = TABLES_IN_SMEM ? smem_f32(c.tab + topic) : __ldg(p.invden + topic);
-              wv = fmul(inv, (float)(v & 0xffffu));
-            }
+            if (lane < sp.size(g)) v = p.rows[rp + sp.begin(g) + lane];
             smem_u32(SV + (g << 5) + lane) = v;
-            smem_f32(WT + (g << 5) + lane) = wv;
           }
           for (int g = 1 + lane; g < nt; g += 32)
             smem_u32(BD + g) = sp.size(g) > 0 ? (p.rows[rp + sp.begin(g)] >> 16) : (uint32_t)K;
@@ -843,13 +830,10 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
                 // the topic the step could not place is inserted there
                 nt = MAXNT;
 #pragma unroll
-                for (int g = 0; g < MAXNT; ++g) {
-                  smem_u32(SV + (g << 5) + lane) = sv[g];
-                  smem_f32(WT + (g << 5) + lane) = wt[g];
-                }
+                for (int g = 0; g < MAXNT; ++g) smem_u32(SV + (g << 5) + lane) = sv[g];
                 if (lane < MAXNT) smem_u32(BD + lane) = (uint32_t)bnd;
                 __syncwarp();
-                wide_insert(c, nt, newt, TABLES_IN_SMEM ? smem_f32(c.tab + newt) : __ldg(p.invden + newt));
+                wide_insert(c, nt, newt);
                 wide = true;
               }
             }
