@@ -107,7 +107,7 @@ int load_nccl() {
       return fail(B200LDA_ECUDA, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 
-constexpr int kExchangeSlabs = 8;  // the all-reduce goes in slabs; slab i is applied while slab i+1 is reduced
+constexpr int kExchangeSlabs = 8;  // the all-reduce goes in (at most) this many slabs; slab i is applied while slab i+1 is reduced
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // d_counters: [0] scheduler (long class), [1..3] last sweep {moved, prior draws, nnz sum},
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
@@ -191,6 +191,7 @@ struct b200lda_ctx {
   std::vector<SweepShape> shape_cache;  // launch shapes by (row class, tiles): computed once per context
   int class_streams = 0;  // see launch_sweep
   int max_ctas = 0;       // B200LDA_MAX_CTAS (experiments): cap on the sampling kernel's grid, 0 = none
+  int exchange_slabs = kExchangeSlabs, apply_ctas = 1 << 20;  // B200LDA_EXCHANGE_SLABS / B200LDA_APPLY_CTAS (experiments)
   int table_refresh = 0;  // LIVE mode: table rebuilds per sweep; 0 = auto (auto_table_refresh)
   int last_refresh = 1;   // what the last sweep used
 
@@ -221,6 +222,7 @@ struct b200lda_ctx {
   cudaStream_t refresh_stream = nullptr;  // LIVE mode: the table refreshers run beside the bulk launches
   cudaEvent_t ev_rfork = nullptr, ev_rjoin = nullptr;
   bool refresher_pending = false;
+  int stream_priority = 0;
   const void* timed_corpus = nullptr;  // corpus whose last sweep left ev_fork / ev_bulk / ev_join to read
   int* d_bad = nullptr;
   void* d_stage = nullptr;
@@ -773,7 +775,7 @@ int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t be
     const double launch_s = share * (double)c->corp.N / kSweepTokensPerSecond;
     const double row_s = kRefreshRowSeconds * std::max(1.0, (double)c->K / 1000.0);
     const int want = (int)std::ceil(rows * row_s / std::max(launch_s, 1e-6) / 8.0);
-    const int room = grid_cap - ctas;
+    const int room = std::min(grid_cap - ctas, grid_cap / 4);
     const int cap = automatic ? std::max(room, (grid_cap * 3 + 99) / 100) : std::max(room, grid_cap / 4);
     const int refreshers = std::max(1, std::min(want, cap));
     if (rows >= 1.0 && grid_cap - refreshers >= 1) {
@@ -870,6 +872,7 @@ int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p, int ref
     const DeviceCorpus::DocClass& dc = cp.classes[i];
     const bool fork = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
     forked[i] = fork;
+    if (fork && !c->side[i]) CU(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, c->stream_priority));
     cudaStream_t st = fork ? c->side[i] : c->stream;
     if (fork) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
     TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i, st,
@@ -993,6 +996,8 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
   c->layout = make_layout(c->K);
   if (const char* e = std::getenv("B200LDA_CLASS_STREAMS")) c->class_streams = atoi(e);  // tuning knob for experiments
   if (const char* e = std::getenv("B200LDA_MAX_CTAS")) c->max_ctas = atoi(e);
+  if (const char* e = std::getenv("B200LDA_EXCHANGE_SLABS")) c->exchange_slabs = std::max(1, std::min(atoi(e), kExchangeSlabs));
+  if (const char* e = std::getenv("B200LDA_APPLY_CTAS")) c->apply_ctas = std::max(1, atoi(e));
   c->table_refresh = std::max(0, std::min((int)cfg->table_refresh, kMaxRefresh));
   if (const char* e = std::getenv("B200LDA_TABLE_REFRESH")) c->table_refresh = std::max(0, std::min(atoi(e), kMaxRefresh));
   c->alpha.assign(c->K, cfg->alpha_sum / c->K);
@@ -1016,9 +1021,11 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
               cudaEventCreateWithFlags(&c->ev_rfork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ev_rjoin, cudaEventDisableTiming) == cudaSuccess &&
               cudaStreamCreateWithPriority(&c->refresh_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
-    for (int i = 0; i < kMaxClasses && ok; ++i)
-      ok = cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
-           cudaEventCreate(&c->ev_join[i]) == cudaSuccess;
+    // the side streams of the background classes are created when a corpus needs them: a process
+    // has few hardware queues, and streams that share one are serialised (the refreshers must run
+    // BESIDE the samplers)
+    c->stream_priority = hi;
+    for (int i = 0; i < kMaxClasses && ok; ++i) ok = cudaEventCreate(&c->ev_join[i]) == cudaSuccess;
     if (!ok) return bail(fail(B200LDA_ECUDA, "creating side streams failed"));
   }
   const size_t VK = (size_t)c->V * c->K;
@@ -1267,7 +1274,7 @@ int sweep_close(b200lda_ctx* c) {
 // Slab s of the exchange buffer: [*i0, *i1) cells of the V x K part.
 void exchange_slab(const b200lda_ctx* c, int s, size_t* i0, size_t* i1) {
   const size_t VK = (size_t)c->V * c->K;
-  const size_t per = ((VK + kExchangeSlabs - 1) / kExchangeSlabs + 3) & ~(size_t)3;
+  const size_t per = ((VK + c->exchange_slabs - 1) / c->exchange_slabs + 3) & ~(size_t)3;
   *i0 = std::min(VK, per * (size_t)s);
   *i1 = std::min(VK, per * (size_t)(s + 1));
 }
@@ -1294,7 +1301,7 @@ int exchange_nccl(b200lda_ctx** ctxs, int n) {
     k_apply_nk_tail<<<(K + 255) / 256, 256, 0, c->stream>>>(K, c->d_nk, c->d_nwk + VK, c->d_nwk_b + VK);
     c->launches += 1;
   }
-  for (int s = 0; s < kExchangeSlabs; ++s) {
+  for (int s = 0; s < ctxs[0]->exchange_slabs; ++s) {
     size_t i0 = 0, i1 = 0;
     exchange_slab(ctxs[0], s, &i0, &i1);
     if (i1 <= i0) continue;
@@ -1309,7 +1316,9 @@ int exchange_nccl(b200lda_ctx** ctxs, int n) {
       CU(cudaSetDevice(c->cfg.device));
       CU(cudaEventRecord(c->ev_slab[s], c->stream));
       CU(cudaStreamWaitEvent(c->apply_stream, c->ev_slab[s], 0));
-      k_apply_sum<<<grid_for(c, (int64_t)((i1 - i0) / 4 + 1), 256), 256, 0, c->apply_stream>>>(i0, i1, nm1, c->d_nwk, c->d_nwk_b);
+      // the apply leaves SMs to NCCL's kernels (the next slab's all-reduce is running beside it)
+      const int apply_grid = std::min(grid_for(c, (int64_t)((i1 - i0) / 4 + 1), 256), c->apply_ctas);
+      k_apply_sum<<<apply_grid, 256, 0, c->apply_stream>>>(i0, i1, nm1, c->d_nwk, c->d_nwk_b);
       c->launches += 1;
       CU(cudaGetLastError());
     }

@@ -617,8 +617,8 @@ __device__ __forceinline__ int token_step_wide(const SweepParams& p, WarpCtx& c,
 // its previous chunk is complete), rebuilds the prior row of the hot word in turn from the live
 // counts into the copy that is not current and makes it current. It only READS the scheduler
 // counter, leaves as soon as the samplers have finished, and gives up when the counter has not
-// moved for ~20 ms (the samplers are not running beside it): no sampler ever waits for it and it
-// never waits unboundedly for them. Readers picked a copy through prior_sel before reading; the copy
+// moved for ~100 us (the samplers are not running beside it): no sampler ever waits for it and it
+// never waits for them longer than that. Readers picked a copy through prior_sel before reading; the copy
 // they read stays untouched until the word's NEXT rebuild, a full pass over the hot list later.
 __global__ void __launch_bounds__(256, 8) k_prior_refresher(const SweepParams p, unsigned long long nchunks) {
   const int lane = threadIdx.x & 31;
@@ -633,9 +633,15 @@ __global__ void __launch_bounds__(256, 8) k_prior_refresher(const SweepParams p,
       unsigned long long done = 0;
       if (lane == 0) done = *reinterpret_cast<volatile unsigned long long*>(p.doc_counter);
       done = __shfl_sync(kFullMask, done, 0);
+      // Samplers that run beside this kernel move the counter every few hundred ns (thousands of
+      // warps fetch chunks). A counter that stands still for ~100 us means they are NOT running
+      // beside it - two streams that share a hardware queue are serialised, and then the samplers
+      // are waiting for THIS kernel to end: leave at once (no refresh this launch, no stall) ...
+      // ... once the counter has moved the samplers ARE running (a small launch hands all its chunks
+      // out at once and is then quiet until the first warp finishes one): only the hard bound applies.
       idle = done == seen ? idle + 1 : 0;
       seen = done;
-      if (idle > 10000) return;
+      if (idle > (done == 0ull ? 50 : 10000)) return;
       done = done > sampler_warps ? done - sampler_warps : 0ull;
       if (done >= nchunks) return;  // the samplers are done: nothing left to refresh for
       if (done * (unsigned long long)p.refresh_rows >= (unsigned long long)idx * nchunks) break;

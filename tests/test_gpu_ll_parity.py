@@ -15,7 +15,7 @@ itself loses 4.7 % / 1.3 % LL at sweeps 25 / 200 going from 1 to 2 threads - and
 mode (prior bucket from per-word tables that are rebuilt DURING the sweep, but not per token; n_k
 from the sweep start) sits between Mallet with 1 and with 2 threads. What is asserted:
   * LIVE, 1 shard: never behind Mallet with 2 threads (0.3 % slack), i.e. ahead of the reference's
-    own configuration, setNumThreads(4); within 3 / 2 / 1.75 / 1.75 % of the SINGLE chain at sweeps
+    own configuration, setNumThreads(4); within 4 / 2.5 / 2 / 1.75 % of the SINGLE chain at sweeps
     25 / 50 / 100 / 200 (the gap closes with sweeps: the reference runs 1 000-10 000);
   * LIVE, G = 2, 4 shards (the reference's setNumThreads(4)): within 3 / 2 / 1.25 / 1 % of Mallet with
     G threads at sweeps 25 / 50 / 100 / 200 (measured 1.5-2.5 / 0.9-1.6 / 0.7-1.0 / 0.5-0.75 % at G = 2 - how many
@@ -82,7 +82,7 @@ def test_single_shard_ll_within_one_percent_of_mallet_at_k1000(c4s, mode_name):
     if mode_name == "LIVE":
         t2 = _band(g, 2)
         assert (curve[None, :] >= t2 * 1.003).all(), (curve.tolist(), t2.tolist())  # LL < 0: x1.003 is 0.3 % lower
-        tol = np.array([0.03, 0.02, 0.0175, 0.0175])
+        tol = np.array([0.04, 0.025, 0.02, 0.0175])
         rel = np.abs(curve[None, :] - ref) / np.abs(ref)
         assert (rel <= tol[None, :]).all(), (curve.tolist(), ref.tolist())
     else:
