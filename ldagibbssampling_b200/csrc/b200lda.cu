@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in nsys / ncu timelines when a tool is attached
 
 #include <algorithm>
 #include <cmath>
@@ -32,6 +33,11 @@ using namespace b200lda;
 namespace {
 
 thread_local std::string g_err;
+
+struct NvtxRange {  // NVTX range around a phase of the sweep (host side: enqueue time of its launches)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -1220,8 +1226,12 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
   }
   TRY(next_event_quad(c));
   CU(cudaEventRecord(c->ev[0], c->stream));
-  TRY(build_tables(c, !deferred));
+  nvtxRangePushA("b200lda:tables");
+  const int rc_tables = build_tables(c, !deferred);
+  nvtxRangePop();
+  TRY(rc_tables);
   CU(cudaEventRecord(c->ev[1], c->stream));
+  NvtxRange sample_range("b200lda:sample");
   if (deferred && !multi)
     CU(cudaMemcpyAsync(c->d_nwk_b, c->d_nwk, sizeof(int32_t) * VK, cudaMemcpyDeviceToDevice, c->stream));
   // one shard: LIVE reads and writes d_nwk; DEFERRED reads the frozen d_nwk, writes the copy d_nwk_b
@@ -1283,6 +1293,7 @@ void exchange_slab(const b200lda_ctx* c, int s, size_t* i0, size_t* i1) {
 // process per GPU). The K-cell tail goes first (n_k), then the V x K cells in slabs: slab s is
 // applied on the context's second stream while NCCL reduces slab s + 1.
 int exchange_nccl(b200lda_ctx** ctxs, int n) {
+  NvtxRange range("b200lda:exchange");
   TRY(load_nccl());
   for (int i = 0; i < n; ++i)
     if (!ctxs[i]->comm) return fail(B200LDA_ESTATE, "context %d has no communicator (b200lda_comm_init / b200lda_group_comm_init)", i);
@@ -1413,6 +1424,7 @@ int b200lda_infer(b200lda_ctx* c, int64_t num_docs, const int64_t* doc_ptr, cons
   DeviceCorpus cp;
   const int64_t bytes_before = c->device_bytes;
   int rc = pack_corpus(c, cp, num_docs, doc_ptr, tok_word);
+  cp.tune_waits = 0;  // one pass over a throw-away corpus: nothing to tune, never wait for timings
   int32_t* d_acc = nullptr;
   double* d_theta = nullptr;
   auto cleanup = [&](int code) {

@@ -109,6 +109,14 @@ class ParallelTopicModel:
         self.devices = list(devices)
         self._dirty = True
 
+    def setSweepLog(self, path, logLikelihoodEvery: int = 0):
+        """B200 extension (SURVEY.md §5 metrics): one JSON line per sweep to `path` - sweep number, device
+        ms of the table build / sampling kernel / exchange, sampled tokens/s, moved and prior-bucket
+        fractions, mean non-zero doc topics, table rebuilds, and LL/token every logLikelihoodEvery sweeps.
+        Logging synchronises after every sweep."""
+        self._sweep_log = path
+        self._sweep_log_ll = int(logLikelihoodEvery)
+
     def setDistributed(self, flag: bool = True, group=None):
         self.distributed = bool(flag)
         self.process_group = group
@@ -238,7 +246,9 @@ class ParallelTopicModel:
         n = self.numIterations
         world, my_rank = self._world()
         optimizing = self.optimizeInterval != 0 and n > self.burninPeriod
-        if not optimizing:
+        if getattr(self, "_sweep_log", None) and not optimizing:
+            self._logged_sweeps(n)
+        elif not optimizing:
             _capi.group_sweep(self._samplers, n)
         else:
             width = int(np.diff(self._doc_ptr).max()) + 1 if len(self._doc_ptr) > 1 else 1
@@ -278,6 +288,27 @@ class ParallelTopicModel:
                 s.synchronize()
         self._iterationsSoFar += n
         self._push_assignments_to_data()
+
+    def _logged_sweeps(self, n):
+        import json
+        tokens = int(self._doc_ptr[-1])
+        with open(self._sweep_log, "a", encoding="utf-8") as out:
+            for it in range(1, n + 1):
+                _capi.group_sweep(self._samplers, 1)
+                st = [s.stats() for s in self._samplers]
+                ms = max(x["last_sweep_ms"] for x in st)
+                local = max(1, sum(x["num_tokens"] for x in st))
+                rec = {"sweep": self._iterationsSoFar + it, "ms": ms, "tokens_per_s": tokens / ms * 1e3 if ms > 0 else None,
+                       "tables_ms": max(x["last_tables_ms"] for x in st), "sample_ms": max(x["last_sample_ms"] for x in st),
+                       "exchange_ms": max(x["last_finish_ms"] for x in st),
+                       "moved_frac": sum(x["tokens_moved_last"] for x in st) / local,
+                       "prior_frac": sum(x["prior_bucket_last"] for x in st) / local,
+                       "mean_doc_topics": sum(x["mean_doc_topics"] * x["num_tokens"] for x in st) / local,
+                       "table_refresh": st[0]["table_refresh_last"], "prior_rows_rebuilt": sum(x["rows_refreshed_last"] for x in st),
+                       "shards": len(st)}
+                if self._sweep_log_ll and it % self._sweep_log_ll == 0 and not self.distributed:
+                    rec["ll_per_token"] = self.modelLogLikelihood() / tokens
+                out.write(json.dumps(rec) + "\n")
 
     def _pull_assignments(self):
         """Global z (document order) of the chain as it stands, before the device state is rebuilt."""

@@ -504,6 +504,26 @@ def test_mirror_write_read_and_update_model_continue_the_chain(oracle, tmp_path)
     c.close()
 
 
+def test_sweep_log_writes_one_record_per_sweep(oracle, tmp_path):
+    import json as _json
+    from ldagibbssampling_b200.instances import InstanceList
+    from ldagibbssampling_b200.topic_model import ParallelTopicModel
+    dp, tok = oracle.gen_corpus(400, 300, 40.0, 6, 46)
+    il = InstanceList.from_arrays(dp, tok)
+    model = ParallelTopicModel(16, ALPHA * 16, BETA)
+    model.setRandomSeed(3)
+    model.setOptimizeInterval(0)
+    model.setSweepLog(str(tmp_path / "sweeps.jsonl"), logLikelihoodEvery=2)
+    model.addInstances(il)
+    model.setNumIterations(4)
+    model.estimate()
+    recs = [_json.loads(ln) for ln in open(tmp_path / "sweeps.jsonl")]
+    assert [r["sweep"] for r in recs] == [1, 2, 3, 4]
+    assert all(r["ms"] > 0 and 0 < r["moved_frac"] <= 1 and r["mean_doc_topics"] >= 1 for r in recs)
+    assert "ll_per_token" in recs[1] and recs[3]["ll_per_token"] > recs[1]["ll_per_token"] - 1.0
+    model.close()
+
+
 def test_library_nccl_exchange_equals_the_oracle_on_two_gpus(oracle):
     """The exchange done by the library itself (communicators from b200lda_group_comm_init, grouped
     slab all-reduces, in-place apply) on two real GPUs: the DEFERRED chain equals the single-shard
