@@ -22,6 +22,8 @@
 //   * count moves: integer RED atomics carry the n_wk moves, n_k moves are accumulated per CTA;
 //   * visit end: the live slots go back to the packed row in ascending topic order through a
 //     K-bit bitmap in shared memory (rank = popcount of the lower bits).
+// Every lane keeps a bit mask of its dead slots, so placing a topic that is new to the document is
+// one ballot (two when its preferred tile is full).
 // token_step<NT> is straight-line code specialised on the tile count (NT = 1..8); rows that can
 // exceed 8 tiles (documents with more than 255 tokens when K > 255) run token_step_wide, the same
 // algorithm with the row in shared memory and loops over tiles.
@@ -334,7 +336,7 @@ __device__ __forceinline__ int bitmap_rank(const WarpCtx& c, int topic) {
 // collectives inside.
 template <int NT, int MAXNT, int MODE, bool LIVE, bool TS, int TE>
 __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint32_t (&sv)[MAXNT], float (&wt)[MAXNT],
-                                          int (&nv)[MAXNT], int& nt, int bnd, uint32_t tok_addr) {
+                                          int (&nv)[MAXNT], int& nt, unsigned& dead, int bnd, uint32_t tok_addr) {
   constexpr bool EXCL = MODE != MODE_INFER;
   const int lane = c.lane;
   const uint4 ta = lds_u128(tok_addr);       // prior row index (LIVE: 2 word + copy, else word), old topic, uniform, Q_w
@@ -415,46 +417,35 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
       if (io | in) {
         sv[g] += in ? 1u : 0xffffffffu;
         wt[g] = fmul(in ? inv_n : inv_o, (float)(sv[g] & 0xffffu));
+        if ((sv[g] & 0xffffu) == 0u) dead |= 1u << g;  // the old topic left the document: its slot is dead
         if (same_word) nvn[g] += in ? 1 : -1;  // the request preceded this token's own count moves
       }
       has_new = has_new || in;
     }
     if (!doc_bucket && !__any_sync(kFullMask, has_new)) {
       // The topic is new to the document: lowest dead lane of its preferred tile (tiles are the
-      // topic ranges fixed at visit start: bnd = first topic of tile `lane`), else of the next tile,
-      // cyclically, that has a dead slot; none anywhere: a new tile's lane 0.
+      // topic ranges fixed at visit start: bnd = first topic of tile `lane`), else the lowest lane
+      // with a dead slot anywhere, at its lowest dead tile; none: a new tile's lane 0.
       const int gstar = __popc(__ballot_sync(kFullMask, newt >= bnd));
-      unsigned dm[NT];
-#pragma unroll
-      for (int g = 0; g < NT; ++g) dm[g] = __ballot_sync(kFullMask, (sv[g] & 0xffffu) == 0u);
-      int gsel = -1, gany = -1;
-      unsigned msel = 0u, many = 0u;
-#pragma unroll
-      for (int g = NT - 1; g >= 0; --g) {
-        if (dm[g]) {
-          gany = g;
-          many = dm[g];
-          if (g >= gstar) {
-            gsel = g;
-            msel = dm[g];
-          }
+      unsigned b = __ballot_sync(kFullMask, (dead >> gstar) & 1u);
+      int mytile = gstar;
+      if (b == 0u) {
+        b = __ballot_sync(kFullMask, dead != 0u);
+        mytile = __ffs(dead) - 1;
+        if (b == 0u) {  // every slot live: append a tile (its registers are already dead slots)
+          if (NT < MAXNT) dead |= 1u << NT;
+          b = NT < MAXNT ? 1u : 0u;  // NT == MAXNT: nt = MAXNT + 1 tells the caller to continue in shared memory
+          mytile = NT;
+          nt = NT + 1;
         }
       }
-      if (gsel < 0) {
-        gsel = gany;
-        msel = many;
-      }
-      if (gsel < 0) {  // every slot live: append a tile (its registers are already dead slots)
-        gsel = NT;
-        msel = NT < MAXNT ? 1u : 0u;  // NT == MAXNT: nt = MAXNT + 1 tells the caller to continue in shared memory
-        nt = NT + 1;
-      }
-      if (lane == __ffs(msel) - 1) {
+      if (lane == __ffs(b) - 1) {
         // the next token's count at the slot's new topic, requested before this token's +1 is issued
         const int fresh = count_load<LIVE>(nrow_next + (uint32_t)newt) + (same_word ? 1 : 0);
+        dead &= ~(1u << mytile);
 #pragma unroll
         for (int g = 0; g < (NT < MAXNT ? NT + 1 : NT); ++g) {
-          if (g == gsel) {
+          if (g == mytile) {
             sv[g] = nkey;
             wt[g] = inv_n;
             if (g < NT) nvn[g] = fresh; else nv[g < MAXNT ? g : 0] = fresh;
@@ -482,8 +473,8 @@ __device__ __forceinline__ int token_step(const SweepParams& p, WarpCtx& c, uint
   return newt;
 }
 
-// Wide path: a topic new to the document takes the lowest dead lane of its preferred tile, else of
-// the next tile (cyclically) that has a dead slot, else lane 0 of an appended tile.
+// Wide path: a topic new to the document takes the lowest dead lane of its preferred tile, else the
+// lowest lane with a dead slot anywhere (at its lowest dead tile), else lane 0 of an appended tile.
 __device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt) {
   const int lane = c.lane;
   const int SV = c.row, BD = c.row + 64 * c.capT;
@@ -491,29 +482,23 @@ __device__ __forceinline__ void wide_insert(const WarpCtx& c, int& nt, int newt)
   int ge = 0;
   for (int g = 1 + lane; g < nt; g += 32) ge += (newt >= (int)smem_u32(BD + g)) ? 1 : 0;
   const int gstar = __reduce_add_sync(kFullMask, ge);
-  int gsel = -1;
-  unsigned msel = 0u;
-  for (int i = 0; i < nt; ++i) {
-    int g = gstar + i;
-    if (g >= nt) g -= nt;
-    const unsigned dm = __ballot_sync(kFullMask, (smem_u32(SV + (g << 5) + lane) & 0xffffu) == 0u);
-    if (dm) {
-      gsel = g;
-      msel = dm;
-      break;
+  int mytile = gstar;
+  unsigned b = __ballot_sync(kFullMask, (smem_u32(SV + (gstar << 5) + lane) & 0xffffu) == 0u);
+  if (b == 0u) {
+    mytile = -1;
+    for (int g = nt - 1; g >= 0; --g)
+      if ((smem_u32(SV + (g << 5) + lane) & 0xffffu) == 0u) mytile = g;
+    b = __ballot_sync(kFullMask, mytile >= 0);
+    if (b == 0u) {  // every slot live: append an empty tile (nt < capT by the class's document lengths)
+      smem_u32(SV + (nt << 5) + lane) = 0u;
+      if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
+      mytile = nt;
+      b = 1u;
+      nt += 1;
+      __syncwarp();
     }
   }
-  if (gsel < 0) {  // every slot live: append an empty tile (nt < capT by the class's document lengths)
-    gsel = nt;
-    msel = 1u;
-    smem_u32(SV + (nt << 5) + lane) = 0u;
-    if (lane == 0) smem_u32(BD + nt) = (uint32_t)c.K;
-    nt += 1;
-    __syncwarp();
-  }
-  if (lane == __ffs(msel) - 1) {
-    smem_u32(SV + (gsel << 5) + lane) = nkey;
-  }
+  if (lane == __ffs(b) - 1) smem_u32(SV + (mytile << 5) + lane) = nkey;
   __syncwarp();
 }
 
@@ -749,6 +734,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
         float wt[MAXNT];
         int nv[MAXNT];
         int bnd = 0x7fffffff;  // register path: first topic of tile `lane` (1 <= lane < nt)
+        unsigned dead = 0u;    // register path: bit g = this lane's slot of tile g (g < nt) is dead
         bool wide = HYBRID && nt > MAXNT;
         if (!wide) {
 #pragma unroll
@@ -756,6 +742,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
             sv[g] = 0u;
             wt[g] = 0.0f;
             nv[g] = 0;
+            if (g < nt && lane >= sp.size(g)) dead |= 1u << g;
             if (g < nt && lane < sp.size(g)) {
               sv[g] = p.rows[rp + sp.begin(g) + lane];
               const int topic = (int)(sv[g] >> 16);
@@ -821,7 +808,7 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
               newt = token_step_wide<MODE, LIVE, TABLES_IN_SMEM>(p, c, nt, c.batch + 8 * t);
             } else {
               // nt is uniform across the warp; instantiations beyond the class's widest row are not generated
-#define B200LDA_STEP(N) token_step<(N <= MAXNT ? N : 1), MAXNT, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, sv, wt, nv, nt, bnd, tok_addr)
+#define B200LDA_STEP(N) token_step<(N <= MAXNT ? N : 1), MAXNT, MODE, LIVE, TABLES_IN_SMEM, kTE>(p, c, sv, wt, nv, nt, dead, bnd, tok_addr)
               if (nt == 1) newt = B200LDA_STEP(1);
               else if (nt == 2) newt = B200LDA_STEP(2);
               else if (nt == 3 || MAXNT == 3) newt = B200LDA_STEP(3);

@@ -187,8 +187,10 @@ int32_t oracle_spec_hsearch(const float* row, int32_t K, float s) {
  *     whenever its count changes); the token being resampled weighs  wt - invden[o]  at its slot;
  *   - a topic leaving the document kills its slot in place; a topic entering it takes the lowest
  *     dead lane of its preferred tile g* = #{g >= 1 : topic >= bound[g]} or, when that tile is
- *     full, of the next tile (cyclically) that has a dead slot, the just-vacated slot included;
- *     when no tile has one, an empty tile is appended (bound = K) and its lane 0 is taken.
+ *     full, the lowest lane that has a dead slot in ANY tile, at that lane's lowest dead tile (the
+ *     just-vacated slot included); when no slot is dead, an empty tile is appended (bound = K) and
+ *     its lane 0 is taken. (Every lane keeps a bit mask of its dead slots: the search is one or
+ *     two ballots.)
  * Tiles therefore stay (mostly) topic ranges, which is what keeps a tile's 32 n_wk gathers on few
  * 128-byte lines; nothing else depends on the placement. At the end of the visit the live slots
  * go back to the document's packed row in ascending topic order. */
@@ -310,16 +312,21 @@ static void row_move(spec_row* r, int32_t K, const float* invden, int32_t o, int
   int32_t gstar = 0;
   for (int32_t g = 1; g < r->nt; ++g)
     if (n >= r->bound[g]) ++gstar;
-  for (int32_t i = 0; i < r->nt; ++i) {
-    const int32_t g = (gstar + i) % r->nt;
-    for (int l = 0; l < 32; ++l)
+  for (int l = 0; l < 32; ++l) /* lowest dead lane of the preferred tile */
+    if (r->count[32 * gstar + l] == 0) {
+      r->topic[32 * gstar + l] = n;
+      r->count[32 * gstar + l] = 1;
+      r->wt[32 * gstar + l] = invden[n];
+      return;
+    }
+  for (int l = 0; l < 32; ++l) /* lowest lane with a dead slot anywhere, its lowest dead tile */
+    for (int32_t g = 0; g < r->nt; ++g)
       if (r->count[32 * g + l] == 0) {
         r->topic[32 * g + l] = n;
         r->count[32 * g + l] = 1;
         r->wt[32 * g + l] = invden[n];
         return;
       }
-  }
   /* every slot is live: append an empty tile, take its lane 0 */
   if (r->nt >= r->cap_tiles) abort();
   memset(r->topic + 32 * r->nt, 0, sizeof(int32_t) * 32);
