@@ -304,3 +304,35 @@ def test_row_growing_past_eight_tiles_moves_to_shared_memory(oracle):
     assert np.diff(rp).max() > 256  # the rows did outgrow the register path
     nwk, nk = oracle.count(dp, tok, want, V, K)
     assert np.array_equal(s.nwk(), nwk) and np.array_equal(s.nk(), nk)
+
+
+def test_live_mode_with_every_warp_on_the_same_word_rows(oracle):
+    """LIVE mode's worst case for own-move visibility: 512 documents over only 12 word types, so the
+    8 warps of every CTA (and every CTA) hammer the same 12 n_wk rows with atomics while reading them
+    through L1. The atomics are exact whatever the reads saw: the counts must equal a recount from z,
+    no count may be negative, and the chain must still improve the likelihood like DEFERRED does."""
+    import ldagibbssampling_b200 as L
+    rng = np.random.default_rng(11)
+    D, V, K = 512, 12, 24
+    lens = rng.integers(40, 200, D).astype(np.int64)
+    dp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = rng.integers(0, V, int(dp[-1])).astype(np.int32)
+    z0 = oracle.init_z(len(tok), K, 2)
+    ll = {}
+    for name, mode, refresh in (("live", L.MODE_LIVE, 1), ("live_refresh", L.MODE_LIVE, 8), ("deferred", L.MODE_DEFERRED, 0)):
+        s = _sampler(K, V, seed=2, mode=mode, table_refresh=refresh)
+        s.load_corpus(dp, tok)
+        s.init_assignments(z0)
+        for _ in range(4):
+            s.sweep(5)
+            z = s.assignments()
+            nwk, nk = oracle.count(dp, tok, z, V, K)
+            g = s.nwk()
+            assert g.min() >= 0 and np.array_equal(g, nwk) and np.array_equal(s.nk(), nk), name
+            assert s.check_invariants() == (len(tok), len(tok), 0, len(tok)), name
+        ll[name] = s.loglik() / len(tok)
+        s.close()
+    ll0 = oracle.loglik(dp, tok, z0, V, K, ALPHA, BETA) / len(tok)
+    assert min(ll.values()) > ll0
+    assert abs(ll["live"] - ll["deferred"]) < 0.02 * abs(ll["deferred"])
+    assert abs(ll["live_refresh"] - ll["deferred"]) < 0.02 * abs(ll["deferred"])
