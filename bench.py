@@ -473,7 +473,16 @@ def b200_arm(args):
         g.init_assignments(cz0)
         g.sweep(t1["ll_after_sweeps"])
         ll_same_corpus = {"corpus": f"the CPU baseline's {args.cpu_docs}-document sample", "sweeps": t1["ll_after_sweeps"],
-                          "cpu_port_T1": t1["ll_per_token"], "b200": g.loglik() / len(ctok)}
+                          "cpu_port_T1": t1["ll_per_token"], "b200": g.loglik() / len(ctok),
+                          "note": "same initial topics, same sweep count; on a corpus this small the early chain is where "
+                                  "the samplers differ most (tests/test_gpu_ll_parity.py follows it to sweep 200)"}
+        if len(info["runs"]) > 1:   # Mallet's own AD-LDA with all host threads, for scale
+            tn = info["runs"][-1]
+            g.sweep(max(0, tn["ll_after_sweeps"] - t1["ll_after_sweeps"]))
+            ll_same_corpus["cpu_port_all_threads"] = {"threads": tn["threads"], "sweeps": tn["ll_after_sweeps"],
+                                                      "ll_per_token": tn["ll_per_token"],
+                                                      "b200_at_that_sweep": g.loglik() / len(ctok)
+                                                      if tn["ll_after_sweeps"] >= t1["ll_after_sweeps"] else None}
         g.close()
 
     if rank == 0:
