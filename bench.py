@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--after-sweeps", type=int, default=50,
                     help="second timed block of --steps sweeps starting at this sweep of the chain (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ll-marks", default="", help="comma-separated sweep counts: also report LL/token of a chain "
+                                                   "started from oracle.init_z(seed 7) at those sweeps (1 GPU)")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -459,6 +461,33 @@ def b200_arm(args):
            "call": "b200lda_load_corpus + b200lda_init_assignments_u16(z) + (count sync) + b200lda_group_sweep(1) "
                    "+ b200lda_get_assignments_u16, pinned host buffers, per rank shard"}
 
+    # ---- LL trajectory in the same run (BASELINE config 1: 500 sweeps against the committed Mallet-port curve)
+    ll_trajectory = None
+    if args.ll_marks and world == 1:
+        from oracle import oracle as O
+        O.build()
+        marks = sorted(int(x) for x in args.ll_marks.split(","))
+        tok_np, dp_np = h_words.numpy(), h_doc_ptr.numpy()
+        g = L.Sampler(K, V, ALPHA_K * K, BETA, seed=7, mode=L.MODE_LIVE if args.mode == "live" else L.MODE_DEFERRED,
+                      device=local_rank)
+        g.load_corpus(dp_np, tok_np)
+        g.init_assignments(O.init_z(len(tok_np), K, 7))
+        done_t, curve = 0, []
+        for mk in marks:
+            g.sweep(mk - done_t)
+            done_t = mk
+            curve.append(g.loglik() / len(tok_np))
+        g.close()
+        ll_trajectory = {"init": "oracle.init_z(N, K, seed=7)", "sweeps": marks, "b200_ll_per_token": curve}
+        gold = os.path.join(ROOT, "tests", "golden", f"{args.workload}_ll_trajectory.json")
+        if os.path.exists(gold) and not args.docs and not args.topics:
+            gj = json.load(open(gold))
+            if gj.get("tokens") == len(tok_np):   # same corpus: the committed Mallet-port curve beside it
+                ll_trajectory["mallet_port"] = {"sweeps": gj["sweeps"], "ll_per_token_by_seed": gj["mallet_ll_per_token"]}
+            else:
+                ll_trajectory["note"] = ("bench_corpus generates this workload on the GPU; the committed Mallet-port curve "
+                                         "(tests/golden) is for the oracle generator's corpus of the same shape")
+
     cpu = None
     ll_same_corpus = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -498,7 +527,7 @@ def b200_arm(args):
                        "corpus_gen_s": gen_s},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "ll_per_token": ll_per_token, "ll_same_corpus": ll_same_corpus,
-            "invariants_ok": bool(invariants_ok), "steady": steady,
+            "invariants_ok": bool(invariants_ok), "steady": steady, "ll_trajectory": ll_trajectory,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

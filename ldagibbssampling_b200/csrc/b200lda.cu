@@ -129,6 +129,7 @@ constexpr size_t kMaxSmemPerCta = 227 * 1024;
 // [4] nnz(n_wk) scratch, [5..7] cumulative {same three}, [8] scheduler (short class)
 constexpr int kCounters = 16;  // [13] corpus checksum scratch;  // [9..11] sink for the stats of inference passes, [12] prior rows rebuilt in the last sweep
 constexpr int kMaxClasses = 16;
+constexpr int kMaxSegments = 32;  // chunk ranges a small corpus's sweep is cut into (full table rebuild between them)
 constexpr int kMaxRefresh = 64;  // table rebuilds per LIVE sweep (b200lda_ctx::table_refresh)
 constexpr int kEventPool = 256;  // sweeps whose device times can be pending before a resolve
 constexpr int kPartial = 1184;   // 148 SMs x 8 blocks: fixed so the LL reduction order is fixed
@@ -210,6 +211,7 @@ struct b200lda_ctx {
   int exchange_slabs = kExchangeSlabs, apply_ctas = 1 << 20;  // B200LDA_EXCHANGE_SLABS / B200LDA_APPLY_CTAS (experiments)
   int table_refresh = 0;  // LIVE mode: table rebuilds per sweep; 0 = auto (auto_table_refresh)
   int last_refresh = 1;   // what the last sweep used
+  int64_t rows_rebuilt_by_host = 0;  // rows rebuilt by the full passes between a small corpus's segments (last sweep)
 
   // counts + tables
   // d_nwk: [V K | K] the counts (+ in multi-shard models a K-cell tail: this shard's n_k moves);
@@ -721,7 +723,14 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
 constexpr double kRefreshRowSeconds = 40.0e-6;
 constexpr double kSweepTokensPerSecond = 3.0e9;
 int auto_table_refresh(const b200lda_ctx* c, const DeviceCorpus& cp) {
-  return (c->hot_count > 0 && cp.N > 0) ? 16 : 1;  // the refreshers' share of the grid bounds what is reached (launch_class)
+  if (c->hot_count <= 0 || cp.N <= 0 || cp.D <= 0) return 1;
+  // The tables only matter for the draws that land in the prior bucket: about
+  // alpha_sum / (alpha_sum + mean document length) of them (measured 0.49 / 0.22 / 0.03 / 0.02 on
+  // C4 / C3 / C2 / C1 against 0.53 / 0.23 / 0.03 / 0.02 from this formula). Below a tenth the age
+  // of the tables is invisible in the chain and the rebuilds are not worth their cost.
+  const double mean_len = (double)cp.N / (double)cp.D;
+  if (c->alpha_sum / (c->alpha_sum + mean_len) < 0.1) return 1;
+  return 16;  // the refreshers' share of the grid (large corpora) / 8 segments (small ones) bound what is reached
 }
 
 // The hot words of the loaded corpus: the most frequent words that together carry 90 % of the
@@ -769,14 +778,20 @@ int build_hot_words(b200lda_ctx* c) {
 template <int MODE, bool LIVE>
 int launch_class(b200lda_ctx* c, SweepParams p, const SweepShape& sh, int64_t begin, int64_t end,
                  unsigned long long* counter, cudaStream_t stream, int max_ctas = 0, int refresh_passes = 0,
-                 unsigned* cursor = nullptr) {
+                 unsigned* cursor = nullptr, int seg = 0, int nseg = 1) {
   if (end <= begin) return B200LDA_OK;
   p.order_begin = begin;
   p.order_end = end;
   p.cap_tiles = sh.cap_tiles;
   p.doc_chunk = sh.doc_chunk;
   p.doc_counter = counter;
-  const int64_t warps_needed = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  // seg / nseg: the launch covers the seg-th of nseg equal ranges of the class's scheduler chunks
+  // (chunks are strided through the longest-first order, so every range is a cross-section)
+  const int64_t all_chunks = (end - begin + sh.doc_chunk - 1) / sh.doc_chunk;
+  p.chunk_begin = (unsigned long long)(all_chunks * seg / nseg);
+  p.chunk_end = (unsigned long long)(all_chunks * (seg + 1) / nseg);
+  if (p.chunk_end <= p.chunk_begin) return B200LDA_OK;
+  const int64_t warps_needed = (int64_t)(p.chunk_end - p.chunk_begin);
   if (c->max_ctas > 0) max_ctas = max_ctas > 0 ? std::min(max_ctas, c->max_ctas) : c->max_ctas;
   const int grid_cap = max_ctas > 0 ? std::min(max_ctas, sh.ctas) : sh.ctas;
   int ctas = (int)std::max<int64_t>(
@@ -878,28 +893,47 @@ int launch_sweep(b200lda_ctx* c, DeviceCorpus& cp, const SweepParams& p, int ref
   retune_background(c, cp);
   if (MODE != MODE_INFER) CU(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
   if (MODE == MODE_UPDATE) CU(cudaMemsetAsync(c->d_counters + 12, 0, sizeof(unsigned long long), c->stream));
-  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses, c->stream));
+  CU(cudaMemsetAsync(c->d_sched, 0, sizeof(unsigned long long) * kMaxClasses * kMaxSegments, c->stream));
   CU(cudaMemsetAsync(c->d_row_cursor, 0, sizeof(unsigned) * kMaxClasses, c->stream));
   const size_t n = cp.classes.size();
   if (n == 0) return B200LDA_OK;
+  // LIVE table refresh, two forms. Large corpora: the refresher kernel beside every bulk launch
+  // (launch_class). Small corpora (a sweep of a few ms: launches too short for a second kernel to be
+  // reliably scheduled beside them, and a full table rebuild costs next to nothing): the bulk classes
+  // run in `segments` chunk ranges with a full rebuild of the tables from the live counts between
+  // them - the rebuild writes every word's other copy and flips its selector, so the background
+  // classes still running on their streams keep reading consistent rows.
+  int segments = 1;
+  if (LIVE && MODE == MODE_UPDATE && refresh_passes > 0 && (double)cp.N / kSweepTokensPerSecond < 5.0e-3) {
+    segments = std::min(refresh_passes + 1, c->table_refresh > 0 ? kMaxSegments : 8);
+    refresh_passes = 0;
+  }
   if (n > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
   // class_streams (B200LDA_CLASS_STREAMS, experiments): 0 = the policy above (default);
   // 1 = everything in sequence; 2 = every class forked at full size.
   std::vector<bool> forked(n, false);
   for (size_t i = 0; i + 1 < n; ++i) {
     const DeviceCorpus::DocClass& dc = cp.classes[i];
-    const bool fork = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
-    forked[i] = fork;
-    if (fork && !c->side[i]) CU(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, c->stream_priority));
-    cudaStream_t st = fork ? c->side[i] : c->stream;
-    if (fork) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-    TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i, st,
-                                  c->class_streams == 0 ? dc.side_ctas : 0, fork ? 0 : refresh_passes,
-                                  c->d_row_cursor + i)));
-    if (fork) CU(cudaEventRecord(c->ev_join[i], st));
+    forked[i] = c->class_streams == 2 || (c->class_streams == 0 && dc.side_ctas > 0);
+    if (!forked[i]) continue;
+    if (!c->side[i]) CU(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, c->stream_priority));
+    CU(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments, c->side[i],
+                                  c->class_streams == 0 ? dc.side_ctas : 0)));
+    CU(cudaEventRecord(c->ev_join[i], c->side[i]));
   }
-  TRY((launch_class<MODE, LIVE>(c, p, cp.classes[n - 1].shape, cp.classes[n - 1].begin, cp.classes[n - 1].end,
-                                c->d_sched + (n - 1), c->stream, 0, refresh_passes, c->d_row_cursor + (n - 1))));
+  for (int seg = 0; seg < segments; ++seg) {
+    if (seg > 0) {
+      TRY(build_tables(c, true));
+      if (MODE == MODE_UPDATE) c->rows_rebuilt_by_host += c->V;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      if (i + 1 < n && forked[i]) continue;
+      const DeviceCorpus::DocClass& dc = cp.classes[i];
+      TRY((launch_class<MODE, LIVE>(c, p, dc.shape, dc.begin, dc.end, c->d_sched + i * kMaxSegments + seg, c->stream, 0,
+                                    refresh_passes, c->d_row_cursor + i, seg, segments)));
+    }
+  }
   if (n > 1) {
     CU(cudaEventRecord(c->ev_bulk, c->stream));
     c->timed_corpus = &cp;
@@ -1067,7 +1101,7 @@ int b200lda_create(const b200lda_config* cfg, b200lda_ctx** out) {
       (rc = dev_alloc_t(c, &c->d_prior, (size_t)(cfg->mode == B200LDA_MODE_LIVE ? 2 : 1) * c->V * c->layout.stride)) ||
       (rc = dev_alloc_t(c, &c->d_q, (size_t)(cfg->mode == B200LDA_MODE_LIVE ? 2 : 1) * c->V)) ||
       (rc = dev_alloc_t(c, &c->d_row_cursor, kMaxClasses)) ||
-      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
+      (rc = dev_alloc_t(c, &c->d_counters, kCounters)) || (rc = dev_alloc_t(c, &c->d_sched, kMaxClasses * kMaxSegments)) || (rc = dev_alloc_t(c, &c->d_bad, 1)) ||
       (rc = dev_alloc_t(c, &c->d_partial, 2 * kPartial + 2)))
     return bail(rc);
   if (cfg->mode == B200LDA_MODE_DEFERRED || multi)
@@ -1279,6 +1313,7 @@ int b200lda_sweep_begin(b200lda_ctx* c) {
     // build_tables above, the others by the refreshers beside the bulk launches
     const int refresh = c->table_refresh > 0 ? c->table_refresh : auto_table_refresh(c, c->corp);
     c->last_refresh = refresh;
+    c->rows_rebuilt_by_host = 0;
     p.prior_sel = c->d_prior_sel;
     p.hot_words = c->d_hot_words;
     p.hot_count = c->hot_count;
@@ -1944,7 +1979,7 @@ int b200lda_get_stats(b200lda_ctx* c, b200lda_stats* out) {
   out->cum_tokens_moved = (int64_t)h[5];
   out->cum_prior_bucket = (int64_t)h[6];
   out->cum_doc_topics = (int64_t)h[7];
-  out->rows_refreshed_last = (int64_t)h[12];
+  out->rows_refreshed_last = (int64_t)h[12] + c->rows_rebuilt_by_host;
   return B200LDA_OK;
 }
 

@@ -81,6 +81,7 @@ struct SweepParams {
   uint32_t sweep;
   int64_t global_tok_off;
   unsigned long long* doc_counter;  // dynamic document scheduler: next chunk index (starts at 0 for each launch)
+  unsigned long long chunk_begin, chunk_end;  // this launch's range of the class's scheduler chunks (a segment of the sweep)
   unsigned long long* stats;        // [0] moved, [1] prior-bucket draws, [2] sum of nnz over tokens (this pass)
   // MODE_INFER: iterations 1..infer_iters per document (Philox sweep key = iteration); a sample is
   // saved when it > burn_in and (it - burn_in) % thinning == 0, or after the last iteration when
@@ -702,9 +703,9 @@ __global__ void __launch_bounds__(256, rowclass_min_ctas(ROWCLASS)) k_gibbs_swee
   const unsigned long long nchunks = (ndocs + (unsigned long long)p.doc_chunk - 1) / (unsigned long long)p.doc_chunk;
   for (;;) {
     unsigned long long ci = 0;
-    if (lane == 0) ci = atomicAdd(p.doc_counter, 1ull);
+    if (lane == 0) ci = p.chunk_begin + atomicAdd(p.doc_counter, 1ull);
     ci = __shfl_sync(kFullMask, ci, 0);
-    if (ci >= nchunks) break;
+    if (ci >= p.chunk_end) break;
 
     for (unsigned long long di = ci; di < ndocs; di += nchunks) {
       // the document's header, read by lane 0 and broadcast: warp-uniform for the compiler too

@@ -11,15 +11,16 @@ sites are estimate() and modelLogLikelihood(), cmu_ron/TrainAndPredict.java:159-
 
 Every assertion is against EACH oracle seed (not the closest one). Measured (profiles/r02_ll_parity.md):
 on a corpus this small AD-LDA with T replicas mixes visibly slower than the single chain - Mallet
-itself loses 4.7 % / 1.3 % LL at sweeps 25 / 200 going from 1 to 2 threads - and the GPU's LIVE
-mode (prior bucket from per-word tables that are rebuilt DURING the sweep, but not per token; n_k
-from the sweep start) sits between Mallet with 1 and with 2 threads. What is asserted:
+itself loses 4.7 % / 1.3 % LL at sweeps 25 / 200 going from 1 to 2 threads. The GPU's LIVE mode
+(prior bucket from per-word tables that are rebuilt DURING the sweep - on a corpus this small: the
+sweep runs in 8 segments with a full rebuild between them -, n_k from the sweep start) follows the
+single chain. What is asserted:
   * LIVE, 1 shard: never behind Mallet with 2 threads (0.3 % slack), i.e. ahead of the reference's
-    own configuration, setNumThreads(4); within 4 / 2.5 / 2 / 1.75 % of the SINGLE chain at sweeps
+    own configuration, setNumThreads(4); within 1.5 / 1 / 1 / 1 % of the SINGLE chain (measured 1.0-1.1 / 0.6 / 0.35 / 0.33 %) at sweeps
     25 / 50 / 100 / 200 (the gap closes with sweeps: the reference runs 1 000-10 000);
-  * LIVE, G = 2, 4 shards (the reference's setNumThreads(4)): within 3 / 2 / 1.25 / 1 % of Mallet with
-    G threads at sweeps 25 / 50 / 100 / 200 (measured 1.5-2.5 / 0.9-1.6 / 0.7-1.0 / 0.5-0.75 % at G = 2 - how many
-    table rebuilds fit a 1 ms sweep depends on timing - and 1.1 / 0.6 / 0.4 / 0.3 % at G = 4);
+  * LIVE, G = 2, 4 shards (the reference's setNumThreads(4)): within 1.5 % of Mallet with G threads at
+    sweep 25 and within 1 % from sweep 50 on (measured 0.8 / 0.5 / 0.25 / 0.2 % at G = 2 and
+    0.4 / 0.15 / 0.1 / 0.1 % at G = 4);
   * DEFERRED is AD-LDA with one replica per DOCUMENT (every other document's counts are a sweep
     old): within 1 % of Mallet with 4 threads from sweep 100 on, never more than 3 % behind it.
 The measured curves are written to gpurun_out/ll_parity_c4s.json when that directory exists.
@@ -82,7 +83,7 @@ def test_single_shard_ll_within_one_percent_of_mallet_at_k1000(c4s, mode_name):
     if mode_name == "LIVE":
         t2 = _band(g, 2)
         assert (curve[None, :] >= t2 * 1.003).all(), (curve.tolist(), t2.tolist())  # LL < 0: x1.003 is 0.3 % lower
-        tol = np.array([0.04, 0.025, 0.02, 0.0175])
+        tol = np.array([0.015, 0.01, 0.01, 0.01])
         rel = np.abs(curve[None, :] - ref) / np.abs(ref)
         assert (rel <= tol[None, :]).all(), (curve.tolist(), ref.tolist())
     else:
@@ -104,4 +105,4 @@ def test_live_shards_ll_within_one_percent_of_mallet_with_as_many_threads(c4s, w
     _record(f"live_{world}", curve)
     for i, mark in enumerate(g["sweeps"]):
         rel = np.abs(curve[i] - ref[:, i]) / np.abs(ref[:, i])
-        assert rel.max() <= {25: 0.03, 50: 0.02, 100: 0.0125}.get(mark, 0.01), (world, mark, curve[i], ref[:, i].tolist())
+        assert rel.max() <= {25: 0.015}.get(mark, 0.01), (world, mark, curve[i], ref[:, i].tolist())
