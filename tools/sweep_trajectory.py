@@ -12,6 +12,8 @@ def main():
     ap.add_argument("--topics", type=int, default=0)
     ap.add_argument("--sweeps", type=int, default=150); ap.add_argument("--every", type=int, default=10)
     ap.add_argument("--mode", default="live")
+    ap.add_argument("--sort-words", action="store_true", help="order every document's tokens by word id before loading "
+                    "(what an in-document word order would do to the n_wk gathers; the library keeps the caller's order)")
     a = ap.parse_args()
     import torch, bench_corpus as BC, ldagibbssampling_b200 as L
     dev = torch.device("cuda", 0)
@@ -19,7 +21,13 @@ def main():
     lengths = BC.doc_lengths(D, w["mean_len"], w["seed"], dev)
     dp = np.zeros(D + 1, np.int64); dp[1:] = torch.cumsum(lengths, 0).cpu().numpy()
     phi = BC.phi_flat_cdf(V, w["k_true"], w["seed"], dev)
-    words = BC.generate_docs(0, D, lengths, phi, V, w["k_true"], w["seed"], dev).cpu().numpy()
+    words = BC.generate_docs(0, D, lengths, phi, V, w["k_true"], w["seed"], dev)
+    if a.sort_words:
+        doc_id = torch.repeat_interleave(torch.arange(D, device=dev), lengths.to(torch.int64))
+        key, _ = torch.sort(doc_id * V + words.to(torch.int64))
+        words = (key % V).to(words.dtype); del key, doc_id
+        print(json.dumps({"repeat_frac": float((words[1:] == words[:-1]).float().mean())}))
+    words = words.cpu().numpy()
     del phi; torch.cuda.empty_cache()
     s = L.Sampler(K, V, 0.1 * K, 0.01, seed=1, mode=L.MODE_LIVE if a.mode == "live" else L.MODE_DEFERRED)
     s.load_corpus(dp, words); s.init_assignments(None)
