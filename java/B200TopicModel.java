@@ -43,7 +43,7 @@ public class B200TopicModel implements Serializable, AutoCloseable {
     return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
   }
 
-  // b200lda_config: int32 x4, double x2, uint64, int32 x4, int64 x2, pointer  (88 bytes)
+  // b200lda_config: int32 x4, double x2, uint64, int32 x4, int64 x2, pointer  (80 bytes, no padding)
   private static final StructLayout CONFIG = MemoryLayout.structLayout(
       JAVA_INT.withName("struct_size"), JAVA_INT.withName("num_topics"), JAVA_INT.withName("num_types"),
       JAVA_INT.withName("mode"), JAVA_DOUBLE.withName("alpha_sum"), JAVA_DOUBLE.withName("beta"),
