@@ -1135,6 +1135,11 @@ void b200lda_destroy(b200lda_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_corpus(c->corp);
+  // the registration goes before the communicator, the communicator before the memory it used
+  if (c->comm && c->nwk_reg && g_nccl.CommDeregister) g_nccl.CommDeregister(c->comm, c->nwk_reg);
+  c->nwk_reg = nullptr;
+  if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
   if (c->nwk_from_nccl && c->d_nwk) {
     g_nccl.MemFree(c->d_nwk);
     c->d_nwk = nullptr;
@@ -1143,9 +1148,6 @@ void b200lda_destroy(b200lda_ctx* c) {
   dev_free(c->d_nwk_b);
   dev_free(c->d_nk);
   dev_free(c->d_nk_delta);
-  if (c->comm && c->nwk_reg && g_nccl.CommDeregister) g_nccl.CommDeregister(c->comm, c->nwk_reg);
-  if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
-  c->comm = nullptr;
   if (c->apply_stream) cudaStreamDestroy(c->apply_stream);
   if (c->ev_applied) cudaEventDestroy(c->ev_applied);
   for (int i = 0; i < kExchangeSlabs; ++i)
@@ -2105,16 +2107,26 @@ int b200lda_group_comm_init(b200lda_ctx** ctxs, int32_t n) {
 
 int b200lda_group_sync_counts(b200lda_ctx** ctxs, int32_t n) {
   if (!ctxs || n < 1) return fail(B200LDA_EINVAL, "bad context list");
+  for (int32_t i = 0; i < n; ++i)
+    if (!ctxs[i]) return fail(B200LDA_EINVAL, "null context");
   if (n == 1 && ctxs[0]->cfg.world_size == 1) return B200LDA_OK;
-  for (int32_t i = 0; i < n; ++i) TRY(b200lda_counts_sync_begin(ctxs[i]));
-  if (ctxs[0]->comm) {
-    const size_t count = (size_t)ctxs[0]->V * ctxs[0]->K + ctxs[0]->K;
-    NCCL(g_nccl.GroupStart());
+  if (n < ctxs[0]->cfg.world_size)  // the other shards live in other processes: only NCCL reaches them
     for (int32_t i = 0; i < n; ++i)
-      NCCL(g_nccl.AllReduce(ctxs[i]->d_nwk, ctxs[i]->d_nwk, count, ncclInt32, ncclSum, ctxs[i]->comm, ctxs[i]->stream));
-    NCCL(g_nccl.GroupEnd());
-  } else {
-    TRY(b200lda_group_allreduce(ctxs, n, B200LDA_BUFFER_EXCHANGE));
+      if (!ctxs[i]->comm)
+        return fail(B200LDA_ESTATE, "%d of %d shards given and context %d has no communicator (b200lda_comm_init)", n,
+                    ctxs[0]->cfg.world_size, i);
+  for (int32_t i = 0; i < n; ++i) {
+    const int rc = b200lda_counts_sync_begin(ctxs[i]);
+    if (rc != B200LDA_OK) {  // nobody stays inside a half-opened sync
+      for (int32_t j = 0; j < i; ++j) ctxs[j]->in_sync = false;
+      return rc;
+    }
+  }
+  // b200lda_group_allreduce: grouped NCCL all-reduces when every context has a communicator, peer copies otherwise
+  const int rc = b200lda_group_allreduce(ctxs, n, B200LDA_BUFFER_EXCHANGE);
+  if (rc != B200LDA_OK) {
+    for (int32_t i = 0; i < n; ++i) ctxs[i]->in_sync = false;
+    return rc;
   }
   for (int32_t i = 0; i < n; ++i) TRY(b200lda_counts_sync_end(ctxs[i]));
   return B200LDA_OK;
