@@ -714,12 +714,12 @@ SweepParams sweep_params(b200lda_ctx* c, const DeviceCorpus& cp, const int32_t* 
 // LIVE mode reads the prior bucket (49 % of the draws at K = 1000, alpha_k = 0.1) from per-word
 // prefix tables. Built once per sweep the chain mixes like Mallet with twice as many threads
 // (LL/token 4 % behind the single chain at sweep 25 on the C4-shaped 20 k-document sample,
-// profiles/r02_ll_parity.md). So in LIVE mode a few CTAs of every bulk launch do not sample but keep
-// rebuilding the rows of the HOT words (those that carry ~90 % of the tokens) from the live counts
-// while the sweep runs (sweep_kernel.cuh: refresher_cta), each `table_refresh` times per sweep in
-// all. A rebuilding warp is busy ~40 us per row (it waits on DRAM for the word's n_wk row), i.e.
-// the refreshers need  rows/s x 40 us  warps.  Auto: up to 16 rebuilds per sweep, as many as 3 % of
-// the grid's CTAs manage (everything a small corpus's idle CTAs manage).
+// profiles/r02_ll_parity.md). So in LIVE mode a small kernel beside every bulk launch (launch_class;
+// sweep_kernel.cuh: k_prior_refresher) keeps rebuilding the rows of the HOT words (those that carry
+// ~90 % of the tokens) from the live counts while the sweep runs, each `table_refresh` times per
+// sweep in all. A rebuilding warp is busy ~40 us per row (it waits on DRAM for the word's n_wk
+// row), i.e. the refreshers need  rows/s x 40 us  warps.  Auto: up to 16 rebuilds per sweep, as many
+// as 3 % of the grid's CTAs manage; small corpora take the segmented form instead (launch_sweep).
 constexpr double kRefreshRowSeconds = 40.0e-6;
 constexpr double kSweepTokensPerSecond = 3.0e9;
 int auto_table_refresh(const b200lda_ctx* c, const DeviceCorpus& cp) {
