@@ -300,6 +300,45 @@ def test_spec_chain_mixes_like_the_mallet_faithful_model(oracle):
         assert lo - slack * abs(lo) <= ll <= hi + 0.01 * abs(hi), (live, ll, mallet)
 
 
+def test_mallet_port_first_draw_follows_the_textbook_conditional(oracle):
+    """Pins the port's s / r / q bucket walk independently of how it was written: the first token a
+    single-threaded sweep resamples sees exactly the initial counts, so over many java.util.Random
+    seeds its new topic must be distributed as the textbook collapsed conditional, the token taken out
+    of n_wk, n_dk AND n_k (exact_conditional is itself pinned to rational arithmetic above). Every document takes a turn as the first one; K = 12 with
+    short documents leaves most topics absent from a document, so all three buckets are drawn from."""
+    rng = np.random.default_rng(7)
+    D, V, K, alpha_sum, beta, draws = 6, 10, 12, 1.8, 0.05, 12000
+    lens = rng.integers(3, 13, D)
+    docs = [rng.integers(0, V, n).astype(np.int32) for n in lens]
+    zs = [rng.integers(0, K, n).astype(np.int32) for n in lens]
+    alpha = [alpha_sum / K] * K
+    worst = 0.0
+    for first in range(D):
+        order = [first] + [d for d in range(D) if d != first]
+        tok = np.concatenate([docs[d] for d in order])
+        z = np.concatenate([zs[d] for d in order])
+        dp = np.zeros(D + 1, np.int64)
+        dp[1:] = np.cumsum([lens[d] for d in order])
+        nwk, nk = oracle.count(dp, tok, z, V, K)
+        ndk = np.bincount(z[:dp[1]], minlength=K)
+        nk_excl = nk.copy()
+        nk_excl[z[0]] -= 1  # Mallet takes the token out of n_k too (the sampling spec of DESIGN.md section 2 does not)
+        p = np.asarray(oracle.exact_conditional(ndk, nwk[tok[0]], nk_excl, alpha, beta, V, int(z[0])))
+        hist = np.zeros(K)
+        for seed in rng.integers(0, 2 ** 31 - 1, draws):
+            m = oracle.MalletModel(K, alpha_sum, beta, seed=int(seed))
+            m.add_instances(dp, tok, V, z_init=z)
+            m.estimate(1)
+            hist[m.assignments()[0]] += 1
+            m.close()
+        freq = hist / draws
+        sigma = np.sqrt(np.maximum(p * (1 - p), 1e-4) / draws)
+        worst = max(worst, float((np.abs(freq - p) / sigma).max()))
+        assert (np.abs(freq - p) < 4.5 * sigma).all(), (first, freq, p)
+        assert hist[p < 1e-12].sum() == 0
+    assert worst > 0.0
+
+
 def test_mallet_init_is_java_random_stream(oracle):
     dp = np.array([0, 4, 9], np.int64)
     tok = np.array([0, 1, 2, 3, 0, 1, 2, 3, 1], np.int32)
