@@ -389,6 +389,35 @@ def test_inferencers_return_distributions(oracle):
     m.close()
 
 
+def test_inferencers_on_a_one_token_document_match_the_closed_form(oracle):
+    """A held-out document of ONE token has a closed-form answer: every sweep draws its topic afresh
+    from p_k ~ alpha_k (n_wk + beta) / (n_k + V beta) on the frozen counts, so the sampled distribution
+    has mean (p_k + alpha_k) / (1 + alpha_sum) whatever iterations / thinning / burn-in are. Pins both
+    the Mallet-faithful inferencer and the spec one (what the GPU runs) to the same number."""
+    D, V, K = 300, 200, 10
+    dp, tok = oracle.gen_corpus(D, V, 40.0, 6, 8)
+    m = oracle.MalletModel(K, ALPHA * K, BETA, seed=5)
+    m.add_instances(dp, tok, V)
+    m.estimate(30)
+    nwk, nk = m.counts()
+    w = int(np.argmax(nwk.sum(1)))  # a frequent word: several topics carry weight
+    p = ALPHA * (nwk[w] + BETA) / (nk + V * BETA)
+    p = p / p.sum()
+    want = (p + ALPHA) / (1 + ALPHA * K)
+    seeds, iters, thin, burn = 1500, 60, 5, 5
+    doc = np.array([w], np.int32)
+    mean_m = np.mean([m.infer(doc, iters, thin, burn, seed=s) for s in range(seeds)], axis=0)
+    ths = oracle.spec_infer(np.arange(seeds + 1, dtype=np.int64), np.full(seeds, w, np.int32), nwk, nk, ALPHA, BETA,
+                            iters, thin, burn, 3)
+    mean_s = np.asarray(ths).mean(0)
+    samples = seeds * ((iters - burn) // thin)  # a lower bound on the draws averaged
+    sigma = np.sqrt(np.maximum(p * (1 - p), 1e-4) / samples) / (1 + ALPHA * K)
+    # consecutive java.util.Random seeds are correlated in their first draws: 6 sigma for the port
+    assert (np.abs(mean_m - want) < 6 * sigma).all(), (mean_m, want)
+    assert (np.abs(mean_s - want) < 5 * sigma).all(), (mean_s, want)
+    m.close()
+
+
 def test_spec_inferencer_agrees_with_the_mallet_faithful_one_within_monte_carlo_error(oracle):
     """TopicInferencer.getSampledDistribution(doc, 100, 10, 10) is a Monte-Carlo estimate of the
     held-out document's posterior theta: one call is noisy (L1 distance between two seeds ~0.3), so the
