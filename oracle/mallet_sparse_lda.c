@@ -19,6 +19,12 @@
  * T worker replicas over contiguous D/T document ranges (last takes the remainder), each
  * rebuilding its replica from its own documents after the sweep, then sum + copy-back.
  * This is also the CPU baseline bench.py times (cpu_baseline.kind = "port").
+ *
+ * What does pin it, short of the jar (tests/test_oracle.py): java.util.Random known answers; the
+ * first draw of a sweep against the textbook conditional over 72 000 seeds; the chain's long-run
+ * state frequencies against the enumerated collapsed posterior on a 243-state corpus; the
+ * inferencer against the closed form of a one-token document; the LL against scipy gammaln.
+ * Those fix the mathematics Mallet implements, not Mallet's byte-for-byte output.
  */
 #include <math.h>
 #include <pthread.h>
