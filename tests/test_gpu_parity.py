@@ -167,6 +167,40 @@ def test_errors_are_reported_not_swallowed(oracle):
         L.Sampler(0, 10, 1.0, 0.1)
 
 
+def test_u16_assignment_paths_equal_the_int32_ones(oracle):
+    """b200lda_init_assignments_u16 / b200lda_get_assignments_u16 (topics in the device's own width,
+    what bench.py's end-to-end step uses) against the int32 entry points: same counts, same rows,
+    same DEFERRED chain; an out-of-range topic is refused and leaves the context usable."""
+    import ldagibbssampling_b200 as L
+    D, V, K = 400, 300, 50
+    dp, tok = oracle.gen_corpus(D, V, 70.0, 12, 21)
+    z0 = oracle.init_z(len(tok), K, 9)
+    a, b = _sampler(K, V, seed=4), _sampler(K, V, seed=4)
+    a.load_corpus(dp, tok)
+    b.load_corpus(dp, tok)
+    a.init_assignments(z0.astype(np.int32))
+    b.init_assignments(z0.astype(np.uint16))
+    assert np.array_equal(a.nwk(), b.nwk()) and np.array_equal(a.nk(), b.nk())
+    for x, y in zip(a.ndk_csr(), b.ndk_csr()):
+        assert np.array_equal(x, y)
+    a.sweep(3)
+    b.sweep(3)
+    za, zb = a.assignments(), b.assignments(np.uint16)
+    assert zb.dtype == np.uint16 and np.array_equal(za, zb.astype(np.int32))
+    assert np.array_equal(za, oracle.spec_sweeps(dp, tok, z0, V, K, ALPHA, BETA, 4, 1, 3))
+    bad = z0.astype(np.uint16)
+    bad[17] = K
+    with pytest.raises(L.B200LDAError) as e:
+        b.init_assignments(bad)
+    assert e.value.code == -6  # ERANGE
+    with pytest.raises(L.B200LDAError):
+        b.sweep(1)  # no valid assignments any more
+    b.init_assignments(z0.astype(np.uint16))
+    assert np.array_equal(b.nwk(), oracle.count(dp, tok, z0, V, K)[0])
+    a.close()
+    b.close()
+
+
 def test_word_order_csr_is_a_permutation_grouped_by_word(oracle):
     D, V, K = 700, 300, 8
     dp, tok = oracle.gen_corpus(D, V, 30.0, 6, 16)
