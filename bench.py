@@ -233,7 +233,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "ll_per_token": info["ll_per_token"],
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -529,13 +529,33 @@ def b200_arm(args):
             "cpu_baseline": cpu, "ll_per_token": ll_per_token, "ll_same_corpus": ll_same_corpus,
             "invariants_ok": bool(invariants_ok), "steady": steady, "ll_trajectory": ll_trajectory,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # stdout carries exactly one line. Native libraries write there too (NCCL prints its version
+    # banner on communicator creation), so file descriptor 1 points at stderr while the arm runs and
+    # the result goes to a duplicate of the original.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
     else:
