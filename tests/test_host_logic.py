@@ -40,6 +40,81 @@ def test_config_struct_matches_the_header_layout():
     assert _capi.Config.global_token_offset.offset == 56 and _capi.Config.stream.offset == 72
 
 
+def _header_prototypes():
+    """{name: (return kind, [argument kinds])} parsed from include/b200lda.h; kinds: ptr, i32, i64, f64, void."""
+    text = open(os.path.join(ROOT, "include", "b200lda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+
+    def kind(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        if re.search(r"\b(int64_t|uint64_t|size_t)\b", decl):
+            return "i64"
+        if re.search(r"\b(int32_t|uint32_t|int)\b", decl):
+            return "i32"
+        if re.search(r"\bdouble\b", decl):
+            return "f64"
+        if decl == "void":
+            return "void"
+        raise AssertionError("unclassified C type: " + decl)
+
+    protos = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][\w\s\*]*?)\b(b200lda_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        args = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        protos[name] = (kind(ret), [kind(a) for a in args])
+    return protos
+
+
+def _ctypes_kind(t):
+    import ctypes as C
+    if t is None:
+        return "void"
+    if t in (C.c_int, C.c_int32, C.c_uint32):
+        return "i32"
+    if t in (C.c_int64, C.c_uint64, C.c_size_t, C.c_longlong, C.c_ulonglong):
+        return "i64"
+    if t is C.c_double:
+        return "f64"
+    return "ptr"  # c_void_p, c_char_p, POINTER(...)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    from ldagibbssampling_b200 import _capi
+    protos = _header_prototypes()
+    assert len(protos) >= 50
+    for name, res, args in _capi.SYMBOLS:
+        want = protos[name]
+        got = (_ctypes_kind(res), [_ctypes_kind(a) for a in args])
+        assert got == want, f"{name}: ctypes {got} vs header {want}"
+
+
+def test_java_shim_descriptors_match_the_header_prototypes():
+    """The Java shim cannot be compiled here (no JDK), so its Panama FunctionDescriptors and the
+    byte offsets it writes b200lda_config at are checked against the header / the ctypes struct."""
+    from ldagibbssampling_b200 import _capi
+    src = open(os.path.join(ROOT, "java", "B200TopicModel.java")).read()
+    protos = _header_prototypes()
+    jkind = {"ADDRESS": "ptr", "JAVA_INT": "i32", "JAVA_LONG": "i64", "JAVA_DOUBLE": "f64"}
+    found = re.findall(r'fn\(\s*"(b200lda_[a-z0-9_]+)"\s*,\s*FunctionDescriptor\.(of|ofVoid)\(([^)]*)\)\)', src)
+    assert len(found) >= 25
+    for name, form, body in found:
+        kinds = [jkind[x.strip()] for x in body.split(",") if x.strip()]
+        got = ("void", kinds) if form == "ofVoid" else (kinds[0], kinds[1:])
+        assert name in protos, f"the shim binds {name}, which the header does not declare"
+        assert got == protos[name], f"{name}: Java {got} vs header {protos[name]}"
+    # cfg.set(LAYOUT, offset, value) calls in rebuildContexts, in field order
+    sets = re.findall(r"cfg\.set\((JAVA_INT|JAVA_LONG|JAVA_DOUBLE|ADDRESS),\s*(\d+),", src)
+    fields = [(n, getattr(_capi.Config, n).offset, _ctypes_kind(t)) for n, t in _capi.Config._fields_]
+    assert len(sets) == len(fields)
+    for (layout, off), (fname, foff, fkind) in zip(sets, fields):
+        assert int(off) == foff and jkind[layout] == fkind, (fname, layout, off, foff, fkind)
+    layout = re.search(r"StructLayout CONFIG = MemoryLayout\.structLayout\((.*?)\);", src, flags=re.S).group(1)
+    names = re.findall(r'withName\("([a-z_0-9]+)"\)', layout)
+    assert names == [n for n, _ in _capi.Config._fields_]
+
+
 def test_no_cpu_fallback_create_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
