@@ -151,7 +151,7 @@ class ParallelTopicModel {
   void setNumIterations(int n) { numIterations = n; }
   void setBurninPeriod(int n) { burninPeriod = n; }
   void setOptimizeInterval(int n) { optimizeInterval = n; }
-  /** = AD-LDA shards = GPUs (devices 0..n-1 unless setDevices). The reference calls it AFTER
+  /** = AD-LDA shards = GPUs (device r mod #GPUs unless setDevices). The reference calls it AFTER
    *  addInstances (cmu_ron/TrainAndPredict.java:162-164): estimate() re-shards, keeping the chain. */
   void setNumThreads(int n) { numThreads = std::max(1, n); }
   void setRandomSeed(int seed) { randomSeed = seed; }
@@ -386,6 +386,10 @@ class ParallelTopicModel {
     const int world = numThreads;
     if (randomSeed == -1) randomSeed = 12345;  // Mallet seeds from the clock; a fixed default keeps runs repeatable
     partition(world);
+    // default placement: shard r on GPU r; with more threads than GPUs (the reference's
+    // setNumThreads(4) on a smaller box) the shards share the GPUs round-robin
+    const int ndev = std::max(1, (int)b200lda_device_count());
+    auto deviceOf = [&](int r) { return devices_.empty() ? r % ndev : devices_.at((size_t)r); };
     for (int r = 0; r < world; ++r) {
       b200lda_config cfg{};
       cfg.struct_size = (int32_t)sizeof(cfg);
@@ -395,7 +399,7 @@ class ParallelTopicModel {
       cfg.alpha_sum = alphaSum;
       cfg.beta = beta;
       cfg.seed = (uint64_t)randomSeed;
-      cfg.device = devices_.empty() ? r : devices_.at((size_t)r);
+      cfg.device = deviceOf(r);
       cfg.rank = r;
       cfg.world_size = world;
       cfg.global_token_offset = shardTok_[(size_t)r];
@@ -429,7 +433,7 @@ class ParallelTopicModel {
       bool distinct = true;
       for (int a = 0; a < world; ++a)
         for (int b = a + 1; b < world; ++b)
-          distinct = distinct && (devices_.empty() ? a != b : devices_.at((size_t)a) != devices_.at((size_t)b));
+          distinct = distinct && deviceOf(a) != deviceOf(b);
       if (distinct) check(b200lda_group_comm_init(ctx_.data(), world));
       // every shard counted its own documents only: sum once (sumTypeTopicCounts at start-up)
       check(b200lda_group_sync_counts(ctx_.data(), world));

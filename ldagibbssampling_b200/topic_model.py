@@ -180,7 +180,13 @@ class ParallelTopicModel:
             import torch
             devices = {my_rank: torch.cuda.current_device()}
         else:
-            devs = self.devices if self.devices is not None else list(range(world))
+            if self.devices is not None:
+                devs = self.devices
+            else:
+                # shard r on GPU r; more threads than GPUs (the reference's setNumThreads(4) on a
+                # smaller box): the shards share the GPUs round-robin, as the Java shim does
+                n_dev = max(1, _capi.device_count())
+                devs = [r % n_dev for r in range(world)]
             if len(devs) != world:
                 raise ValueError("setDevices needs one device per thread/shard")
             devices = dict(zip(ranks, devs))
